@@ -1,0 +1,233 @@
+"""mbpol_b200 -- host-side mirror of the reference's MB-pol call surface over libmbpol_b200.so.
+
+The product is the C-ABI library (include/mbpol_b200.h, csrc/); this module is the thin Python binding the
+tests and bench.py use, named after the reference's own entry points:
+
+    reference (Fortran, mbpol.f90)                    here
+    ------------------------------------------------  ---------------------------------------------
+    call mbpol_init(nrite, nttm2)          :52-85     h = mbpol_init(nttm2, flags=..., device=...)
+    call mbpol_forces(imcon,cell,nttm2,listttm2,      out = mbpol_forces(h, imcon, cell, nttm2, listttm2,
+         wat_monomer_ener,xxx,yyy,zzz,fxx,fyy,fzz,          xxx, yyy, zzz, fxx, fyy, fzz, engsrp, virsrp, stress, ...)
+         engsrp,virsrp,stress)             :98-116
+    call mbpol_fini()                      :89-94     mbpol_fini(h)
+    mbpol_2b_poly_/mbpol_3b_poly_ (C ABI)             mbpol_2b_poly / mbpol_3b_poly (same arguments, arrays in/out)
+
+There is NO CPU fallback: importing works anywhere (so the CPU test-suite can check the ABI), but every compute
+entry point raises if the CUDA library cannot be loaded or no sm_100 GPU is present.
+(The directory name contains '-', so import it through the `mbpol_b200` shim module at the repository root.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmbpol_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "mbpol_b200.h")
+
+WANT_ATOMIC_ENERGY, WANT_FDECOMP, WANT_ATOMIC_STRESS = 1, 2, 4
+DEFAULT_FLAGS = 3
+ENGUNIT = 418.4
+FLOP_PER_DIMER, FLOP_PER_TRIMER = 30601, 111818     # counted flops of the reference bodies
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lib = None
+
+
+class MBPolError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libmbpol_b200.so (built by __graft_entry__.build() / csrc/Makefile).  Fails loudly when missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MBPolError("libmbpol_b200.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.mbpol_b200_last_error.restype = C.c_char_p
+        lib.mbpol_b200_stream.restype = C.c_void_p
+        lib.mbpol_b200_init.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        for name in ("mbpol_b200_fini", "mbpol_b200_compute", "mbpol_b200_last_error", "mbpol_b200_stream"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.mbpol_b200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def _p(a, dtype=np.float64):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous, "arrays must be contiguous %s" % dtype
+    return a.ctypes.data_as(_dp if dtype == np.float64 else _ip)
+
+
+class Handle:
+    def __init__(self, ptr, nttm2, flags):
+        self.ptr, self.nttm2, self.flags = ptr, nttm2, flags
+
+
+def _check(h, rc, what):
+    if rc:
+        msg = load_library().mbpol_b200_last_error(h.ptr if h else None)
+        raise MBPolError("%s failed with status %d: %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def mbpol_cutoffs():
+    a, b = C.c_double(), C.c_double()
+    load_library().mbpol_b200_cutoffs(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def mbpol_init(nttm2, flags=DEFAULT_FLAGS, device=-1):
+    """mbpol.f90:52-85.  nttm2 = 3 * number of waters."""
+    lib = load_library()
+    ptr = C.c_void_p()
+    rc = lib.mbpol_b200_init(int(nttm2), int(device), int(flags), C.byref(ptr))
+    if rc:
+        raise MBPolError("mbpol_b200_init failed with status %d (4 = no sm_100 GPU, 2 = CUDA error)" % rc)
+    return Handle(ptr, int(nttm2), int(flags))
+
+
+def mbpol_fini(h):
+    """mbpol.f90:89-94."""
+    if h.ptr:
+        load_library().mbpol_b200_fini(h.ptr)
+        h.ptr = None
+
+
+def mbpol_set_shard(h, rank, nranks):
+    _check(h, load_library().mbpol_b200_set_shard(h.ptr, int(rank), int(nranks)), "mbpol_b200_set_shard")
+
+
+def mbpol_forces(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, fxx, fyy, fzz, engsrp=0.0, virsrp=0.0, stress=None,
+                 atomic_energy=None, atomic_stress=None, atomic_fdecomp=None, vxx=None, vyy=None, vzz=None):
+    """The drop-in for mbpol_forces (mbpol.f90:98-449): accumulates into fxx/fyy/fzz/stress and the per-atom arrays
+    in place and returns a dict with the updated engsrp/virsrp, the four partial scalars and the flux partials."""
+    lib = load_library()
+    sc = [C.c_double(0.0) for _ in range(4)]
+    if stress is None:
+        stress = np.zeros(9)
+    jflux = np.zeros(9)
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    rc = lib.mbpol_b200_forces(h.ptr, C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32),
+                               C.c_int(len(xxx)), _p(xxx), _p(yyy), _p(zzz), _p(fxx), _p(fyy), _p(fzz),
+                               C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]), C.byref(sc[3]), _p(stress),
+                               _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz), _p(jflux))
+    _check(h, rc, "mbpol_b200_forces")
+    eng2, vir2, eng3, vir3 = (s.value for s in sc)
+    return {"eng2": eng2, "vir2": vir2, "eng3": eng3, "vir3": vir3, "engsrp": engsrp + eng2 + eng3,
+            "virsrp": virsrp + vir2 + vir3, "stress": stress, "jflux": jflux}
+
+
+def mbpol_upload(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, vxx=None, vyy=None, vzz=None):
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    rc = load_library().mbpol_b200_upload(h.ptr, C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32),
+                                          C.c_int(len(xxx)), _p(xxx), _p(yyy), _p(zzz), _p(vxx), _p(vyy), _p(vzz))
+    _check(h, rc, "mbpol_b200_upload")
+
+
+def mbpol_compute(h):
+    _check(h, load_library().mbpol_b200_compute(h.ptr), "mbpol_b200_compute")
+
+
+def mbpol_download(h, fxx, fyy, fzz, stress=None, atomic_energy=None, atomic_stress=None, atomic_fdecomp=None):
+    sc = [C.c_double(0.0) for _ in range(4)]
+    if stress is None:
+        stress = np.zeros(9)
+    jflux = np.zeros(9)
+    rc = load_library().mbpol_b200_download(h.ptr, _p(fxx), _p(fyy), _p(fzz), C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]),
+                                            C.byref(sc[3]), _p(stress), _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp),
+                                            _p(jflux))
+    _check(h, rc, "mbpol_b200_download")
+    eng2, vir2, eng3, vir3 = (s.value for s in sc)
+    return {"eng2": eng2, "vir2": vir2, "eng3": eng3, "vir3": vir3, "stress": stress, "jflux": jflux}
+
+
+def mbpol_device_outputs(h):
+    """(device pointer, element count) of the packed FP64 output buffer -- for an NCCL all-reduce."""
+    ptr, cnt = C.c_void_p(), C.c_longlong()
+    _check(h, load_library().mbpol_b200_device_outputs(h.ptr, C.byref(ptr), C.byref(cnt)), "mbpol_b200_device_outputs")
+    return ptr.value, cnt.value
+
+
+def mbpol_stream(h):
+    return load_library().mbpol_b200_stream(h.ptr)
+
+
+def mbpol_counts(h):
+    v = [C.c_longlong() for _ in range(4)]
+    _check(h, load_library().mbpol_b200_counts(h.ptr, *[C.byref(x) for x in v]), "mbpol_b200_counts")
+    return {"dimers": v[0].value, "trimers": v[1].value, "dimers_shard": v[2].value, "trimers_shard": v[3].value}
+
+
+def mbpol_lists(h):
+    c = mbpol_counts(h)
+    d = np.zeros((max(c["dimers"], 1), 2), dtype=np.int32)
+    t = np.zeros((max(c["trimers"], 1), 3), dtype=np.int32)
+    rc = load_library().mbpol_b200_get_lists(h.ptr, _p(d, np.int32), C.c_longlong(c["dimers"]), _p(t, np.int32), C.c_longlong(c["trimers"]))
+    _check(h, rc, "mbpol_b200_get_lists")
+    return d[:c["dimers"]], t[:c["trimers"]]
+
+
+def mbpol_kernel_times(h):
+    ms = (C.c_float * 4)()
+    n = C.c_longlong()
+    _check(h, load_library().mbpol_b200_kernel_times(h.ptr, ms, C.byref(n)), "mbpol_b200_kernel_times")
+    return {"lists_ms": ms[0], "k2b_ms": ms[1], "k3b_ms": ms[2], "total_ms": ms[3], "launches": n.value}
+
+
+def mbpol_eval_dimers(w, want_fm=True):
+    """Batched mbpol_2b_poly_: w [n,18] imaged coordinates -> E[n], g[n,18], fm[n,6,6,3] (kcal/mol)."""
+    w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 18)
+    n = len(w)
+    E, g = np.zeros(n), np.zeros((n, 18))
+    fm = np.zeros((n, 108)) if want_fm else None
+    rc = load_library().mbpol_b200_eval_dimers(C.c_int(n), _p(w), _p(E), _p(g), _p(fm))
+    if rc:
+        raise MBPolError("mbpol_b200_eval_dimers failed with status %d" % rc)
+    return E, g, (fm.reshape(n, 6, 6, 3) if want_fm else None)
+
+
+def mbpol_eval_trimers(w, want_fm=True):
+    w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 27)
+    n = len(w)
+    E, g = np.zeros(n), np.zeros((n, 27))
+    fm = np.zeros((n, 243)) if want_fm else None
+    rc = load_library().mbpol_b200_eval_trimers(C.c_int(n), _p(w), _p(E), _p(g), _p(fm))
+    if rc:
+        raise MBPolError("mbpol_b200_eval_trimers failed with status %d" % rc)
+    return E, g, (fm.reshape(n, 9, 9, 3) if want_fm else None)
+
+
+def mbpol_2b_poly(w1, w2):
+    """The legacy symbol itself, mbpol-2b-poly.cpp:1888-1893."""
+    w1 = np.ascontiguousarray(w1, dtype=np.float64); w2 = np.ascontiguousarray(w2, dtype=np.float64)
+    E = C.c_double()
+    g1, g2, fm = np.zeros(9), np.zeros(9), np.zeros(108)
+    load_library().mbpol_2b_poly_(_p(w1), _p(w2), C.byref(E), _p(g1), _p(g2), _p(fm))
+    return E.value, g1, g2, fm.reshape(6, 6, 3)
+
+
+def mbpol_3b_poly(w1, w2, w3):
+    """The legacy symbol itself, mbpol-3b-poly.cpp:1526-1531 (gradients are accumulated into zeroed arrays)."""
+    w = [np.ascontiguousarray(v, dtype=np.float64) for v in (w1, w2, w3)]
+    E = C.c_double()
+    g1, g2, g3, fm = np.zeros(9), np.zeros(9), np.zeros(9), np.zeros(243)
+    load_library().mbpol_3b_poly_(_p(w[0]), _p(w[1]), _p(w[2]), C.byref(E), _p(g1), _p(g2), _p(g3), _p(fm))
+    return E.value, g1, g2, g3, fm.reshape(9, 9, 3)
+
+
+def run_box(h, box, want_stress=False, want_fdecomp=True, with_velocities=True):
+    """Convenience for tests/bench: one mbpol_forces call on a synth box with fresh (zeroed) accumulators."""
+    n = int(box["mxatms"])
+    out = {k: np.zeros(n) for k in ("fxx", "fyy", "fzz", "atomic_energy")}
+    out["atomic_stress"] = np.zeros(9 * n) if want_stress else None
+    out["atomic_fdecomp"] = np.zeros(9 * n) if want_fdecomp else None
+    v = (box["vxx"], box["vyy"], box["vzz"]) if with_velocities else (None, None, None)
+    r = mbpol_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"],
+                     out["fxx"], out["fyy"], out["fzz"], stress=np.zeros(9), atomic_energy=out["atomic_energy"],
+                     atomic_stress=out["atomic_stress"], atomic_fdecomp=out["atomic_fdecomp"], vxx=v[0], vyy=v[1], vzz=v[2])
+    out.update(r)
+    return out

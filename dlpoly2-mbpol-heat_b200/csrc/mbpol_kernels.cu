@@ -1,0 +1,958 @@
+// mbpol_kernels.cu -- libmbpol_b200.so: kernels + C ABI (include/mbpol_b200.h).  sm_100a only, FP64.
+//
+// Pipeline of one mbpol_forces-equivalent step (reference: mbpol.f90:98-449), all on one stream:
+//   K0  k_gather_image      xxx/yyy/zzz + listttm2 -> imaged monomers, SoA [9][nw]            (mbpol.f90:184-196, 1275-1301)
+//   K1a k_cell_index/k_cell_fill   counting sort of waters into cells (oxygen positions)
+//   K1b k_neighbours        27-cell search with the reference's exact predicates -> per-water neighbour rows
+//   K1c k_fill_dimers, k_count_trimers, k_fill_trimers (+ cub exclusive scans) -> compact (i,j) / (i,j,k) lists
+//   K2  k_dimers            2B energy/gradient (+ pair matrix for HEAT_STRESS), scatter     (mbpol.f90:453-790)
+//   K3  k_trimers           3B energy/gradient, scatter                                      (mbpol.f90:794-1271)
+//   K5  k_flux              sum_i e_i v_i, sum_i S_i v_i, sum_i W_i v_i                       (heatcurrent.f90:464-483, 703-728)
+// Scatter: FP64 red.global.add into the packed output buffer; scalars are block-reduced first.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mbpol_b200.h"
+#include "mbpol_device.cuh"
+#include "gen/mbpol_model_data.h"
+
+__constant__ double mbpol_coef2b[1153];
+__constant__ double mbpol_coef3b[1163];
+__constant__ MbpolParams mbpol_par;
+
+namespace {
+
+constexpr int NB2_CAP = 96;    // neighbours j>i within r2f (6.5 A): ~19 on average in liquid water
+constexpr int NB3_CAP = 40;    // neighbours within r3f (4.5 A): ~13 on average
+constexpr int NSCAL = 32;
+enum { S_ENG2 = 0, S_VIR2 = 1, S_ENG3 = 2, S_VIR3 = 3, S_STRESS = 4, S_JFLUX = 13, S_ND = 22, S_NT = 23 };
+
+struct OutPtrs {      // views into the packed output buffer
+    double *fx, *fy, *fz, *aeng, *astress, *afd, *scal;
+    int mxatms;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// K0: gather + image_monomers.  mono[c*nw + m], c = 0..8 (O xyz, H1 xyz, H2 xyz)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_gather_image(int nw, const int* __restrict__ list, const double* __restrict__ x, const double* __restrict__ y,
+                               const double* __restrict__ z, CellInfo C, double* __restrict__ mono)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nw) return;
+    double w[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int i = list[3 * m + a] - 1;
+        w[3 * a] = x[i]; w[3 * a + 1] = y[i]; w[3 * a + 2] = z[i];
+    }
+#pragma unroll
+    for (int h = 1; h < 3; ++h) {
+        double dx = __dsub_rn(w[3 * h], w[0]), dy = __dsub_rn(w[3 * h + 1], w[1]), dz = __dsub_rn(w[3 * h + 2], w[2]);
+        image_vec(C, dx, dy, dz);
+        w[3 * h] = __dadd_rn(w[0], dx); w[3 * h + 1] = __dadd_rn(w[1], dy); w[3 * h + 2] = __dadd_rn(w[2], dz);
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) mono[(size_t)c * nw + m] = w[c];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1a: cells.  Fractional coordinates s = rcell * r wrapped to [0,1); cell edge >= r2f in every direction, so all
+// partners within either cutoff sit in the 27 surrounding cells.  The grid is only a candidate filter: membership is
+// decided by the exact predicates in k_neighbours.
+// ---------------------------------------------------------------------------------------------------------
+struct Grid { int nc[3]; double rc[9]; };
+
+__device__ __forceinline__ int cell_of(const Grid& G, double x, double y, double z, int* cxyz)
+{
+    double s[3] = {G.rc[0] * x + G.rc[3] * y + G.rc[6] * z, G.rc[1] * x + G.rc[4] * y + G.rc[7] * z, G.rc[2] * x + G.rc[5] * y + G.rc[8] * z};
+    int c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s[k] -= floor(s[k]);
+        c[k] = min(max((int)(s[k] * G.nc[k]), 0), G.nc[k] - 1);
+        if (cxyz) cxyz[k] = c[k];
+    }
+    return (c[2] * G.nc[1] + c[1]) * G.nc[0] + c[0];
+}
+
+__global__ void k_cell_index(int nw, const double* __restrict__ mono, Grid G, int* __restrict__ cell_id, int* __restrict__ cell_count)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nw) return;
+    const int c = cell_of(G, mono[m], mono[(size_t)nw + m], mono[2 * (size_t)nw + m], nullptr);
+    cell_id[m] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+__global__ void k_cell_fill(int nw, const int* __restrict__ cell_id, const int* __restrict__ cell_start, int* __restrict__ cell_fill,
+                            int* __restrict__ sorted)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nw) return;
+    const int c = cell_id[m];
+    sorted[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1b: neighbour rows.  Thread per water i (taken in cell order so a warp works on one neighbourhood).
+//   nb2[i][*]: j > i with  r^2 <= r2f^2     (reject: r^2 .gt. r2f**2, mbpol.f90:502)
+//   nb3[i][*]: j != i with sqrt(r^2) <= r3f (reject: r .gt. r3f,      mbpol.f90:865-869)
+// d = O_min(i,j) - O_max(i,j), then the reference's minimum image.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C, Grid G, const int* __restrict__ cell_start,
+                             const int* __restrict__ sorted, int* __restrict__ nb2, int* __restrict__ n2, int* __restrict__ nb3,
+                             int* __restrict__ n3, int* __restrict__ overflow)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nw) return;
+    const int i = sorted[t];
+    const double xi = mono[i], yi = mono[(size_t)nw + i], zi = mono[2 * (size_t)nw + i];
+    int ci[3];
+    cell_of(G, xi, yi, zi, ci);
+    const double r2f2 = __dmul_rn(mbpol_par.r2f, mbpol_par.r2f);
+    int c2 = 0, c3 = 0;
+    int lo[3], cnt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // unique neighbour cells even when the grid is narrower than 3
+        cnt[k] = min(G.nc[k], 3);
+        lo[k] = (G.nc[k] >= 3) ? ci[k] - 1 : 0;
+    }
+    for (int dz = 0; dz < cnt[2]; ++dz)
+        for (int dy = 0; dy < cnt[1]; ++dy)
+            for (int dx = 0; dx < cnt[0]; ++dx) {
+                const int cx = (lo[0] + dx + G.nc[0]) % G.nc[0], cy = (lo[1] + dy + G.nc[1]) % G.nc[1], cz = (lo[2] + dz + G.nc[2]) % G.nc[2];
+                const int c = (cz * G.nc[1] + cy) * G.nc[0] + cx;
+                for (int p = cell_start[c]; p < cell_start[c + 1]; ++p) {
+                    const int j = sorted[p];
+                    if (j == i) continue;
+                    const double xj = mono[j], yj = mono[(size_t)nw + j], zj = mono[2 * (size_t)nw + j];
+                    double ddx, ddy, ddz;
+                    if (i < j) { ddx = __dsub_rn(xi, xj); ddy = __dsub_rn(yi, yj); ddz = __dsub_rn(zi, zj); }
+                    else       { ddx = __dsub_rn(xj, xi); ddy = __dsub_rn(yj, yi); ddz = __dsub_rn(zj, zi); }
+                    image_vec(C, ddx, ddy, ddz);
+                    const double rsq = norm2_exact(ddx, ddy, ddz);
+                    if (j > i && !(rsq > r2f2)) {
+                        if (c2 < NB2_CAP) nb2[(size_t)i * NB2_CAP + c2] = j;
+                        ++c2;
+                    }
+                    if (!(__dsqrt_rn(rsq) > mbpol_par.r3f)) {
+                        if (c3 < NB3_CAP) nb3[(size_t)i * NB3_CAP + c3] = j;
+                        ++c3;
+                    }
+                }
+            }
+    if (c2 > NB2_CAP || c3 > NB3_CAP) atomicExch(overflow, 1);
+    n2[i] = min(c2, NB2_CAP);
+    n3[i] = min(c3, NB3_CAP);
+}
+
+__global__ void k_fill_dimers(int nw, const int* __restrict__ nb2, const int* __restrict__ n2, const long long* __restrict__ off,
+                              int2* __restrict__ dimers)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nw) return;
+    const long long o = off[i];
+    for (int q = 0; q < n2[i]; ++q) dimers[o + q] = make_int2(i, nb2[(size_t)i * NB2_CAP + q]);
+}
+
+// A triple is accepted iff at least two of its three O-O distances are <= r3f (mbpol.f90:865-869).  Enumerate it from
+// a centre c that is within r3f of both others; when all three pairs are close every water is such a centre and the
+// triple is emitted from the smallest index only.
+__device__ __forceinline__ bool in_row(const int* __restrict__ row, int n, int v)
+{
+    for (int q = 0; q < n; ++q)
+        if (row[q] == v) return true;
+    return false;
+}
+
+template <bool FILL>
+__global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* __restrict__ n3, long long* __restrict__ cnt,
+                               const long long* __restrict__ off, int* __restrict__ trimers)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nw) return;
+    const int* row = nb3 + (size_t)c * NB3_CAP;
+    const int n = n3[c];
+    long long k = 0;
+    const long long base = FILL ? off[c] : 0;
+    for (int p = 0; p < n; ++p)
+        for (int q = p + 1; q < n; ++q) {
+            const int a = row[p], b = row[q];
+            const bool closed = in_row(nb3 + (size_t)a * NB3_CAP, n3[a], b);
+            if (closed && !(c < a && c < b)) continue;
+            if (FILL) {
+                int t0 = c, t1 = a, t2 = b, s;
+                if (t0 > t1) { s = t0; t0 = t1; t1 = s; }
+                if (t1 > t2) { s = t1; t1 = t2; t2 = s; }
+                if (t0 > t1) { s = t0; t0 = t1; t1 = s; }
+                int* o = trimers + 3 * (base + k);
+                o[0] = t0; o[1] = t1; o[2] = t2;
+            }
+            ++k;
+        }
+    if (!FILL) cnt[c] = k;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// block reduction of NV per-thread doubles -> atomicAdd into dst[0..NV)
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* dst)
+{
+    __shared__ double red[NV][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) red[k][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = lane < nwarp ? red[k][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) atomicAdd(dst + k, x);
+        }
+    }
+}
+
+// per-atom force-decomposition tensor W (heatcurrent.f90:529-533, 703-728):
+//   W_i(a,b) += (n*x_i - sum_j x_j)_a^raw * f_b ,  f = -g_i*engunit/n
+__device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, const double* xraw_i, const double* xsum, int n,
+                                                const double* f)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double ra = n * xraw_i[a] - xsum[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) atomicAdd(O.afd + atom + (size_t)O.mxatms * (a + 3 * b), ra * f[b]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: trimers.  One thread per accepted trimer of this shard.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
+          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
+    if (t < ntri) {
+        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
+        double r[27];
+        // imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
+        double wj[9], wi[9], wk[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            wi[c] = mono[(size_t)c * nw + mi];
+            wj[c] = mono[(size_t)c * nw + mj];
+            wk[c] = mono[(size_t)c * nw + mk];
+        }
+        double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+        double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
+        image_vec(C, a0, a1, a2);
+        image_vec(C, b0, b1, b2);
+        const double ra[3] = {a0, a1, a2}, rb[3] = {b0, b1, b2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            r[c] = ra[c];                               // O_i' - O_j
+            r[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+            r[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+            r[9 + c] = 0.0;
+            r[12 + c] = wj[3 + c] - wj[c];
+            r[15 + c] = wj[6 + c] - wj[c];
+            r[18 + c] = -rb[c];                         // O_k' - O_j
+            r[21 + c] = (wk[3 + c] - wk[c]) - rb[c];
+            r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
+        }
+        double E, cv[36];
+        trimer_eval(r, E, cv);
+        double g[27];
+        trimer_gradient(r, cv, g);
+        const double eu = MBPOL_ENGUNIT;
+        const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
+        sc[0] = E * eu;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const int atom = o[a / 3] - 1 + (a % 3);
+            const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
+            atomicAdd(O.fx + atom, -gx);
+            atomicAdd(O.fy + atom, -gy);
+            atomicAdd(O.fz + atom, -gz);
+            sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
+            sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
+            sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
+        }
+        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
+            const double e9 = (1.0 / 9.0) * E * eu;
+#pragma unroll
+            for (int a = 0; a < 9; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e9);
+        }
+        if (flags & MBPOL_B200_WANT_FDECOMP) {
+            double xs[3] = {0, 0, 0}, xraw[27];
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+                const int atom = o[a / 3] - 1 + (a % 3);
+                xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
+                xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
+            }
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+                const double f[3] = {-(1.0 / 9.0) * g[3 * a] * eu, -(1.0 / 9.0) * g[3 * a + 1] * eu, -(1.0 / 9.0) * g[3 * a + 2] * eu};
+                scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 9, f);
+            }
+        }
+        if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {
+            // S_i(a,b) = 1/2*eu*sum_{j != i} (r_i-r_j)_a FM[i][j]_b with FM[i][j] = cv_n (r_i - r_j): a symmetric
+            // tensor cv_n d (x) d that goes to BOTH atoms of variable n (mbpol.f90:945-966)
+            double S[9][6];
+#pragma unroll
+            for (int a = 0; a < 9; ++a)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) S[a][q] = 0.0;
+#pragma unroll
+            for (int n = 0; n < 36; ++n) {
+                const int a = V3A[n], b = V3B[n];
+                const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
+                const double h = 0.5 * eu * cv[n];
+                const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
+            }
+            const size_t n = O.mxatms;
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+                double* p = O.astress + o[a / 3] - 1 + (a % 3);
+                atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
+                atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
+                atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
+            }
+        }
+    }
+    // scalars: eng3, vir3, stress (symmetric fill: 2,3,4 / 3?,...)  -> scal[S_ENG3], scal[S_VIR3], scal[S_STRESS+..]
+    double v2[2] = {sc[0], sc[1]};
+    block_reduce_add<2>(v2, O.scal + S_ENG3);
+    __syncthreads();
+    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
+    block_reduce_add<9>(st, O.scal + S_STRESS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: dimers
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
+         const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < ndim) {
+        const int mi = dim[t].x, mj = dim[t].y;
+        double wi[9], wj[9], w[18];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            wi[c] = mono[(size_t)c * nw + mi];
+            wj[c] = mono[(size_t)c * nw + mj];
+        }
+        double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+        image_vec(C, a0, a1, a2);                       // do_dimer, mbpol.f90:496-509; origin moved to O_j
+        const double ra[3] = {a0, a1, a2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            w[c] = ra[c];
+            w[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+            w[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+            w[9 + c] = 0.0;
+            w[12 + c] = wj[3 + c] - wj[c];
+            w[15 + c] = wj[6 + c] - wj[c];
+        }
+        double E, g[18];
+        double fm[108];
+        const bool want_s = (flags & MBPOL_B200_WANT_ATOMIC_STRESS) != 0;
+        dimer_eval(w, E, g, want_s ? fm : nullptr);
+        const double eu = MBPOL_ENGUNIT;
+        const int o[2] = {list[3 * mi], list[3 * mj]};
+        sc[0] = E * eu;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const int atom = o[a / 3] - 1 + (a % 3);
+            const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
+            atomicAdd(O.fx + atom, -gx);
+            atomicAdd(O.fy + atom, -gy);
+            atomicAdd(O.fz + atom, -gz);
+            sc[1] += w[3 * a] * gx + w[3 * a + 1] * gy + w[3 * a + 2] * gz;
+            sc[2] -= w[3 * a] * gx; sc[3] -= w[3 * a] * gy; sc[4] -= w[3 * a] * gz;
+            sc[5] -= w[3 * a + 1] * gy; sc[6] -= w[3 * a + 1] * gz; sc[7] -= w[3 * a + 2] * gz;
+        }
+        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
+            const double e6 = (1.0 / 6.0) * E * eu;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e6);
+        }
+        if (flags & MBPOL_B200_WANT_FDECOMP) {
+            double xs[3] = {0, 0, 0}, xraw[18];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const int atom = o[a / 3] - 1 + (a % 3);
+                xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
+                xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double f[3] = {-(1.0 / 6.0) * g[3 * a] * eu, -(1.0 / 6.0) * g[3 * a + 1] * eu, -(1.0 / 6.0) * g[3 * a + 2] * eu};
+                scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 6, f);
+            }
+        }
+        if (want_s) {   // mbpol.f90:558-579: S_i(a,b) = 1/2*eu*sum_{j != i} (r_i - r_j)_a * FM[i][j]_b  (FM is NOT antisymmetric)
+            const size_t n = O.mxatms;
+            for (int i = 0; i < 6; ++i) {
+                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 6; ++j) {
+                    if (i == j) continue;
+                    for (int a = 0; a < 3; ++a) {
+                        const double ra_ = w[3 * i + a] - w[3 * j + a];
+                        for (int b = 0; b < 3; ++b) S[a + 3 * b] += ra_ * fm[18 * i + 3 * j + b];
+                    }
+                }
+                double* p = O.astress + o[i / 3] - 1 + (i % 3);
+                for (int q = 0; q < 9; ++q) atomicAdd(p + n * q, 0.5 * eu * S[q]);
+            }
+        }
+    }
+    double v2[2] = {sc[0], sc[1]};
+    block_reduce_add<2>(v2, O.scal + S_ENG2);
+    __syncthreads();
+    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
+    block_reduce_add<9>(st, O.scal + S_STRESS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: heat-flux contractions over the atoms of THIS shard's partial sums (linear, so partials add up)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_flux(int natoms_real, OutPtrs O, const double* __restrict__ vx, const double* __restrict__ vy,
+                       const double* __restrict__ vz, int flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double j[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < natoms_real) {
+        const double v[3] = {vx[i], vy[i], vz[i]};
+        const size_t n = O.mxatms;
+        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
+            const double e = O.aeng[i];
+            j[0] = e * v[0]; j[1] = e * v[1]; j[2] = e * v[2];
+        }
+        if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {   // compute_heat_flux reads the upper triangle only (heatcurrent.f90:475-480)
+            const double* s = O.astress + i;
+            const double s11 = s[0], s12 = s[n * 3], s13 = s[n * 6], s22 = s[n * 4], s23 = s[n * 7], s33 = s[n * 8];
+            j[3] = s11 * v[0] + s12 * v[1] + s13 * v[2];
+            j[4] = s12 * v[0] + s22 * v[1] + s23 * v[2];
+            j[5] = s13 * v[0] + s23 * v[1] + s33 * v[2];
+        }
+        if (flags & MBPOL_B200_WANT_FDECOMP) {
+            const double* w = O.afd + i;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) j[6 + a] = w[n * (a + 0)] * v[0] + w[n * (a + 3)] * v[1] + w[n * (a + 6)] * v[2];
+        }
+    }
+    block_reduce_add<9>(j, O.scal + S_JFLUX);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched per-cluster kernels (legacy ABI / KAT tests)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double ww[18], gg[18], e, f[108];
+    for (int i = 0; i < 18; ++i) ww[i] = w[(size_t)18 * t + i];
+    dimer_eval(ww, e, gg, fm ? f : nullptr);
+    E[t] = e;
+    for (int i = 0; i < 18; ++i) g[(size_t)18 * t + i] = gg[i];
+    if (fm)
+        for (int i = 0; i < 108; ++i) fm[(size_t)108 * t + i] = f[i];
+}
+
+__global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double r[27], cv[36], gg[27], e;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) r[i] = w[(size_t)27 * t + i];
+    trimer_eval(r, e, cv);
+    trimer_gradient(r, cv, gg);
+    E[t] = e;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) g[(size_t)27 * t + i] = gg[i];
+    if (fm) {
+        double* f = fm + (size_t)243 * t;
+        for (int i = 0; i < 243; ++i) f[i] = 0.0;
+#pragma unroll
+        for (int n_ = 0; n_ < 36; ++n_) {
+            const int a = V3A[n_], b = V3B[n_];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double d = cv[n_] * (r[3 * a + c] - r[3 * b + c]);
+                f[27 * a + 3 * b + c] = d;
+                f[27 * b + 3 * a + c] = -d;
+            }
+        }
+    }
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+std::once_flag g_const_once[16];
+
+#define CUDA_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                  \
+            return MBPOL_B200_ECUDA;                                                                        \
+        }                                                                                                   \
+    } while (0)
+
+void invert3(const double* a, double* b, double& d)   // invert.f
+{
+    b[0] = a[4] * a[8] - a[5] * a[7]; b[1] = a[2] * a[7] - a[1] * a[8]; b[2] = a[1] * a[5] - a[2] * a[4];
+    b[3] = a[5] * a[6] - a[3] * a[8]; b[4] = a[0] * a[8] - a[2] * a[6]; b[5] = a[2] * a[3] - a[0] * a[5];
+    b[6] = a[3] * a[7] - a[4] * a[6]; b[7] = a[1] * a[6] - a[0] * a[7]; b[8] = a[0] * a[4] - a[1] * a[3];
+    d = a[0] * b[0] + a[3] * b[1] + a[6] * b[2];
+    double r = 0.0;
+    if (std::fabs(d) > 0.0) r = 1.0 / d;
+    for (int i = 0; i < 9; ++i) b[i] = r * b[i];
+}
+
+int upload_constants(int device)
+{
+    MbpolParams P;
+    const double k2[8] = {MBPOL_P2b_k_HH_intra, MBPOL_P2b_k_OH_intra, MBPOL_P2b_k_HH_coul, MBPOL_P2b_k_OH_coul,
+                          MBPOL_P2b_k_OO_coul, MBPOL_P2b_k_XH_main, MBPOL_P2b_k_XO_main, MBPOL_P2b_k_XX_main};
+    std::copy(k2, k2 + 8, P.k2);
+    P.gamma_in = MBPOL_P2b_in_plane_gamma; P.gamma_out = MBPOL_P2b_out_of_plane_gamma;
+    P.r2i = MBPOL_P2b_r2i; P.r2f = MBPOL_P2b_r2f;
+    const double k3[5] = {MBPOL_P3b_kHH_intra, MBPOL_P3b_kOH_intra, MBPOL_P3b_kHH, MBPOL_P3b_kOH, MBPOL_P3b_kOO};
+    const double d3[5] = {MBPOL_P3b_dHH_intra, MBPOL_P3b_dOH_intra, MBPOL_P3b_dHH, MBPOL_P3b_dOH, MBPOL_P3b_dOO};
+    std::copy(k3, k3 + 5, P.k3); std::copy(d3, d3 + 5, P.d3);
+    P.r3i = MBPOL_P3b_r3i; P.r3f = MBPOL_P3b_r3f;
+    (void)device;
+    if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(mbpol_coef2b, MBPOL_COEF2B_HOST, sizeof(double) * MBPOL_NCOEF2B) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(mbpol_coef3b, MBPOL_COEF3B_HOST, sizeof(double) * MBPOL_NCOEF3B) != cudaSuccess) return 1;
+    return 0;
+}
+
+int ensure_constants(int device)
+{
+    static int status[16] = {0};
+    if (device < 0 || device >= 16) return 1;
+    std::call_once(g_const_once[device], [&]() { status[device] = upload_constants(device); });
+    return status[device];
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+struct mbpol_b200_handle {
+    int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1;
+    int mxatms = 0, imcon = 0;
+    bool have_vel = false, uploaded = false;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    CellInfo C;
+    Grid G;
+    int ncells = 0;
+    DevBuf<double> xyz, vel, mono, out;
+    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag;
+    DevBuf<int2> dimers;
+    DevBuf<long long> off2, off3, cnt3, n2ll;
+    DevBuf<char> scan_tmp;
+    std::vector<double> host_out;
+    double* pinned = nullptr;
+    size_t pinned_cap = 0;
+    long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
+    float ms[4] = {0, 0, 0, 0};
+    size_t out_count() const { return (size_t)22 * mxatms + NSCAL; }
+    OutPtrs views()
+    {
+        OutPtrs O;
+        const size_t n = mxatms;
+        O.fx = out.p; O.fy = out.p + n; O.fz = out.p + 2 * n; O.aeng = out.p + 3 * n;
+        O.astress = out.p + 4 * n; O.afd = out.p + 13 * n; O.scal = out.p + 22 * n; O.mxatms = mxatms;
+        return O;
+    }
+};
+
+namespace {
+__global__ void k_widen(int n, const int* __restrict__ a, long long* __restrict__ b)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+
+int scan_ll(mbpol_b200_handle* h, const long long* in, long long* out, int n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream);
+    CUDA_TRY(h, h->scan_tmp.reserve(bytes));
+    CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, bytes, in, out, n, h->stream));
+    return 0;
+}
+int scan_int(mbpol_b200_handle* h, const int* in, int* out, int n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream);
+    CUDA_TRY(h, h->scan_tmp.reserve(bytes));
+    CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, bytes, in, out, n, h->stream));
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle)
+{
+    if (!handle || nttm2 < 3 || nttm2 % 3) return MBPOL_B200_EINVAL;
+    *handle = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MBPOL_B200_ENODEVICE;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MBPOL_B200_ENODEVICE;
+    if (device >= ndev) return MBPOL_B200_EINVAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return MBPOL_B200_ENODEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return MBPOL_B200_ECUDA;
+    if (ensure_constants(device)) return MBPOL_B200_ECUDA;
+    auto* h = new mbpol_b200_handle;
+    h->device = device; h->nw = nttm2 / 3; h->flags = flags;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    *handle = h;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_fini(mbpol_b200_handle* h)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MBPOL_B200_OK;
+}
+
+const char* mbpol_b200_last_error(const mbpol_b200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void mbpol_b200_cutoffs(double* r2f, double* r3f) { *r2f = MBPOL_P2b_r2f; *r3f = MBPOL_P3b_r3f; }
+
+int mbpol_b200_set_shard(mbpol_b200_handle* h, int rank, int nranks)
+{
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks) return MBPOL_B200_EINVAL;
+    h->rank = rank; h->nranks = nranks;
+    return MBPOL_B200_OK;
+}
+
+void* mbpol_b200_stream(mbpol_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int nttm2, const int* listttm2, int mxatms,
+                      const double* xxx, const double* yyy, const double* zzz, const double* vxx, const double* vyy, const double* vzz)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (imcon < 1 || imcon > 3 || !cell || nttm2 != 3 * h->nw || !listttm2 || mxatms < nttm2 || !xxx || !yyy || !zzz) {
+        h->err = "mbpol_b200_upload: invalid argument (imcon must be 1, 2 or 3; nttm2 must match init)";
+        return MBPOL_B200_EINVAL;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->mxatms = mxatms; h->imcon = imcon;
+    const size_t n = mxatms;
+    CellInfo& C = h->C;
+    C.imcon = imcon;
+    std::copy(cell, cell + 9, C.cell);
+    double det;
+    invert3(cell, C.rcell, det);
+    C.a1 = 1.0 / cell[0]; C.b1 = 1.0 / cell[4]; C.c1 = 1.0 / cell[8];
+    // candidate grid: fractional coordinates through the inverse cell; for imcon 1/2 the cell is diagonal
+    double gc[9] = {0};
+    if (imcon == 1) { gc[0] = gc[4] = gc[8] = cell[0]; }
+    else if (imcon == 2) { gc[0] = cell[0]; gc[4] = cell[4]; gc[8] = cell[8]; }
+    else std::copy(cell, cell + 9, gc);
+    double grc[9], gdet;
+    invert3(gc, grc, gdet);
+    if (!(std::fabs(gdet) > 0.0)) { h->err = "singular cell"; return MBPOL_B200_EINVAL; }
+    std::copy(grc, grc + 9, h->G.rc);
+    const double rcut = MBPOL_P2b_r2f * 1.0001;
+    h->ncells = 1;
+    for (int k = 0; k < 3; ++k) {   // perpendicular width of the cell along reciprocal vector k = 1/|row k of inverse|
+        const double len = std::sqrt(grc[k] * grc[k] + grc[3 + k] * grc[3 + k] + grc[6 + k] * grc[6 + k]);
+        int nc = (int)std::floor((1.0 / len) / rcut);
+        nc = std::max(1, std::min(nc, 1024));
+        h->G.nc[k] = nc;
+        h->ncells *= nc;
+    }
+    CUDA_TRY(h, h->xyz.reserve(3 * n));
+    CUDA_TRY(h, h->list.reserve(nttm2));
+    CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p, xxx, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + n, yyy, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + 2 * n, zzz, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->list.p, listttm2, (size_t)nttm2 * 4, cudaMemcpyHostToDevice, h->stream));
+    h->have_vel = vxx && vyy && vzz;
+    if (h->have_vel) {
+        CUDA_TRY(h, h->vel.reserve(3 * n));
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p, vxx, n * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + n, vyy, n * 8, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + 2 * n, vzz, n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->uploaded = true;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_compute(mbpol_b200_handle* h)
+{
+    if (!h || !h->uploaded) return MBPOL_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nw = h->nw;
+    const size_t n = h->mxatms;
+    cudaStream_t s = h->stream;
+    const int TB = 128, gb = (nw + TB - 1) / TB;
+    h->launches = 0;
+    CUDA_TRY(h, h->mono.reserve(9 * (size_t)nw));
+    CUDA_TRY(h, h->out.reserve(h->out_count()));
+    CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw));
+    CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
+    CUDA_TRY(h, h->nb2.reserve((size_t)nw * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)nw * NB3_CAP));
+    CUDA_TRY(h, h->n2.reserve(nw)); CUDA_TRY(h, h->n3.reserve(nw)); CUDA_TRY(h, h->flag.reserve(1));
+    CUDA_TRY(h, h->off2.reserve(nw + 1)); CUDA_TRY(h, h->off3.reserve(nw + 1)); CUDA_TRY(h, h->cnt3.reserve(nw + 1));
+    CUDA_TRY(h, h->n2ll.reserve(nw + 1));
+
+    CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
+    CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_count() * 8, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->cell_cnt.p, 0, (size_t)(h->ncells + 1) * 4, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->cell_fill.p, 0, (size_t)(h->ncells + 1) * 4, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->flag.p, 0, 4, s));
+    k_gather_image<<<gb, TB, 0, s>>>(nw, h->list.p, h->xyz.p, h->xyz.p + n, h->xyz.p + 2 * n, h->C, h->mono.p);
+    k_cell_index<<<gb, TB, 0, s>>>(nw, h->mono.p, h->G, h->cell_id.p, h->cell_cnt.p);
+    if (int rc = scan_int(h, h->cell_cnt.p, h->cell_cnt.p, h->ncells + 1)) return rc;   // in-place exclusive scan -> cell_start
+    k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->sorted.p);
+    k_neighbours<<<gb, TB, 0, s>>>(nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
+    k_widen<<<(nw + 1 + TB - 1) / TB, TB, 0, s>>>(nw, h->n2.p, h->n2ll.p);
+    CUDA_TRY(h, cudaMemsetAsync(h->n2ll.p + nw, 0, 8, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->cnt3.p + nw, 0, 8, s));
+    if (int rc = scan_ll(h, h->n2ll.p, h->off2.p, nw + 1)) return rc;
+    k_trimers_enum<false><<<gb, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, h->cnt3.p, nullptr, nullptr);
+    if (int rc = scan_ll(h, h->cnt3.p, h->off3.p, nw + 1)) return rc;
+    h->launches += 9;
+    long long tot[2];
+    int ovf = 0;
+    CUDA_TRY(h, cudaMemcpyAsync(&tot[0], h->off2.p + nw, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&tot[1], h->off3.p + nw, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&ovf, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (ovf) { h->err = "neighbour capacity exceeded (NB2_CAP/NB3_CAP): unphysical density"; return MBPOL_B200_ECAPACITY; }
+    h->nd_total = tot[0]; h->nt_total = tot[1];
+    CUDA_TRY(h, h->dimers.reserve((size_t)std::max<long long>(tot[0], 1)));
+    CUDA_TRY(h, h->trimers.reserve((size_t)std::max<long long>(3 * tot[1], 3)));
+    k_fill_dimers<<<gb, TB, 0, s>>>(nw, h->nb2.p, h->n2.p, h->off2.p, h->dimers.p);
+    k_trimers_enum<true><<<gb, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, nullptr, h->off3.p, h->trimers.p);
+    h->launches += 2;
+    CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
+
+    // contiguous shard of each list (the analogue of the bead_rank/bead_size stride, mbpol.f90:218-226, 311-314)
+    const long long d0 = tot[0] * h->rank / h->nranks, d1 = tot[0] * (h->rank + 1) / h->nranks;
+    const long long t0 = tot[1] * h->rank / h->nranks, t1 = tot[1] * (h->rank + 1) / h->nranks;
+    h->nd_shard = d1 - d0; h->nt_shard = t1 - t0;
+    OutPtrs O = h->views();
+    const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
+    if (h->nd_shard > 0) {
+        k_dimers<<<(unsigned)((h->nd_shard + 255) / 256), 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        ++h->launches;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
+    if (h->nt_shard > 0) {
+        k_trimers<<<(unsigned)((h->nt_shard + 255) / 256), 256, 0, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        ++h->launches;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
+    if (h->have_vel) {
+        const int nreal = 3 * nw;   // the O/H atoms; compute_heat_flux2 loops 1..3*mxatms/4 (heatcurrent.f90:710)
+        k_flux<<<(nreal + 255) / 256, 256, 0, s>>>(nreal, O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
+        ++h->launches;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev[4], s));
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->ms[3], h->ev[0], h->ev[4]);
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* fzz, double* eng2, double* vir2, double* eng3,
+                        double* vir3, double* stress, double* atomic_energy, double* atomic_stress, double* atomic_fdecomp, double* jflux)
+{
+    if (!h || !h->uploaded || !fxx || !fyy || !fzz) return MBPOL_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t n = h->mxatms, cnt = h->out_count();
+    if (h->pinned_cap < cnt) {
+        if (h->pinned) cudaFreeHost(h->pinned);
+        h->pinned = nullptr; h->pinned_cap = 0;
+        CUDA_TRY(h, cudaMallocHost(&h->pinned, cnt * 8));
+        h->pinned_cap = cnt;
+    }
+    double* P = h->pinned;
+    // copy only what the caller asked for
+    CUDA_TRY(h, cudaMemcpyAsync(P, h->out.p, (atomic_energy ? 4 : 3) * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (atomic_stress) CUDA_TRY(h, cudaMemcpyAsync(P + 4 * n, h->out.p + 4 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (atomic_fdecomp) CUDA_TRY(h, cudaMemcpyAsync(P + 13 * n, h->out.p + 13 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, NSCAL * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) { fxx[i] += P[i]; fyy[i] += P[n + i]; fzz[i] += P[2 * n + i]; }
+    if (atomic_energy) for (size_t i = 0; i < n; ++i) atomic_energy[i] += P[3 * n + i];
+    if (atomic_stress) for (size_t i = 0; i < 9 * n; ++i) atomic_stress[i] += P[4 * n + i];
+    if (atomic_fdecomp) for (size_t i = 0; i < 9 * n; ++i) atomic_fdecomp[i] += P[13 * n + i];
+    const double* sc = P + 22 * n;
+    if (eng2) *eng2 += sc[S_ENG2];
+    if (vir2) *vir2 += sc[S_VIR2];
+    if (eng3) *eng3 += sc[S_ENG3];
+    if (vir3) *vir3 += sc[S_VIR3];
+    if (stress) for (int q = 0; q < 9; ++q) stress[q] += sc[S_STRESS + q];
+    if (jflux) for (int q = 0; q < 9; ++q) jflux[q] = sc[S_JFLUX + q];
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_forces(mbpol_b200_handle* h, int imcon, const double* cell, int nttm2, const int* listttm2, int mxatms,
+                      const double* xxx, const double* yyy, const double* zzz, double* fxx, double* fyy, double* fzz, double* eng2,
+                      double* vir2, double* eng3, double* vir3, double* stress, double* atomic_energy, double* atomic_stress,
+                      double* atomic_fdecomp, const double* vxx, const double* vyy, const double* vzz, double* jflux)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (atomic_stress && !(h->flags & MBPOL_B200_WANT_ATOMIC_STRESS)) {
+        h->err = "atomic_stress requested but the handle was created without MBPOL_B200_WANT_ATOMIC_STRESS";
+        return MBPOL_B200_EINVAL;
+    }
+    if (int rc = mbpol_b200_upload(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, vxx, vyy, vzz)) return rc;
+    if (int rc = mbpol_b200_compute(h)) return rc;
+    return mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+}
+
+int mbpol_b200_device_outputs(mbpol_b200_handle* h, void** dev_ptr, long long* count)
+{
+    if (!h || !h->out.p) return MBPOL_B200_EINVAL;
+    *dev_ptr = h->out.p;
+    *count = (long long)h->out_count();
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_counts(mbpol_b200_handle* h, long long* ndt, long long* ntt, long long* nds, long long* nts)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (ndt) *ndt = h->nd_total;
+    if (ntt) *ntt = h->nt_total;
+    if (nds) *nds = h->nd_shard;
+    if (nts) *nts = h->nt_shard;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_get_lists(mbpol_b200_handle* h, int* dimers, long long dimer_cap, int* trimers, long long trimer_cap)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (dimers && dimer_cap >= h->nd_total && h->nd_total > 0)
+        CUDA_TRY(h, cudaMemcpy(dimers, h->dimers.p, (size_t)h->nd_total * 8, cudaMemcpyDeviceToHost));
+    if (trimers && trimer_cap >= h->nt_total && h->nt_total > 0)
+        CUDA_TRY(h, cudaMemcpy(trimers, h->trimers.p, (size_t)h->nt_total * 12, cudaMemcpyDeviceToHost));
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (ms) std::copy(h->ms, h->ms + 4, ms);
+    if (launches) *launches = h->launches;
+    return MBPOL_B200_OK;
+}
+
+// ---- batched per-cluster API -----------------------------------------------------------------------------
+static int eval_clusters(int n, int nat3, const double* w, double* E, double* g, double* fm, int fmlen)
+{
+    if (n <= 0 || !w || !E || !g) return MBPOL_B200_EINVAL;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return MBPOL_B200_ENODEVICE;
+    if (ensure_constants(device)) return MBPOL_B200_ECUDA;
+    double *dw = nullptr, *dE = nullptr, *dg = nullptr, *dfm = nullptr;
+    int rc = MBPOL_B200_OK;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess) rc = MBPOL_B200_ECUDA; return e == cudaSuccess; };
+    if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
+        (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
+        if (nat3 == 18) k_eval_dimers<<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm);
+        else k_eval_trimers<<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm);
+        ok(cudaGetLastError());
+        ok(cudaDeviceSynchronize());
+        ok(cudaMemcpy(E, dE, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(g, dg, (size_t)n * nat3 * 8, cudaMemcpyDeviceToHost));
+        if (fm) ok(cudaMemcpy(fm, dfm, (size_t)n * fmlen * 8, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dw); cudaFree(dE); cudaFree(dg); cudaFree(dfm);
+    return rc;
+}
+
+int mbpol_b200_eval_dimers(int n, const double* w, double* E, double* g, double* fm) { return eval_clusters(n, 18, w, E, g, fm, 108); }
+int mbpol_b200_eval_trimers(int n, const double* w, double* E, double* g, double* fm) { return eval_clusters(n, 27, w, E, g, fm, 243); }
+
+// ---- the reference's per-cluster symbols -----------------------------------------------------------------
+void mbpol_2b_poly_(const double* w1, const double* w2, double* E, double* g1, double* g2, double* force_matrix)
+{
+    double w[18], g[18];
+    std::copy(w1, w1 + 9, w); std::copy(w2, w2 + 9, w + 9);
+    if (mbpol_b200_eval_dimers(1, w, E, g, force_matrix) != MBPOL_B200_OK) { *E = std::nan(""); return; }
+    std::copy(g, g + 9, g1); std::copy(g + 9, g + 18, g2);      // assigned, like mbpol-2b-poly.cpp:660-663
+}
+
+void mbpol_3b_poly_(const double* w1, const double* w2, const double* w3, double* E, double* g1, double* g2, double* g3,
+                    double* force_matrix)
+{
+    double w[27], g[27];
+    std::copy(w1, w1 + 9, w); std::copy(w2, w2 + 9, w + 9); std::copy(w3, w3 + 9, w + 18);
+    if (mbpol_b200_eval_trimers(1, w, E, g, force_matrix) != MBPOL_B200_OK) { *E = std::nan(""); return; }
+    for (int i = 0; i < 9; ++i) { g1[i] += g[i]; g2[i] += g[9 + i]; g3[i] += g[18 + i]; }   // accumulated, mbpol-3b-poly.cpp:39-40
+}
+
+void mbpol_2b_cutoff_(double* r) { *r = MBPOL_P2b_r2f; }
+void mbpol_3b_cutoff_(double* r) { *r = MBPOL_P3b_r3f; }
+
+}  // extern "C"
