@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py -- MB-pol 2B+3B force + per-atom heat-flux decomposition step on B200(s), next to the CPU reference.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU evaluators on the host cores)
+
+One "step" = one complete mbpol_forces-equivalent evaluation (mbpol.f90:98-449) of a synthetic water box:
+GPU cell-list build of the dimer/trimer lists, 2B and 3B polynomial energies + gradients, scatter of forces,
+per-atom energy and force-decomposition tensor, heat-flux contractions, and (N>1) one NCCL all-reduce of the packed
+output buffer.  `value` = accepted trimers of the box / step time with inputs resident in HBM (CUDA events on the
+library's stream, max over ranks); `e2e` = the same through the public mbpol_forces call with host buffers
+(H2D of coordinates/velocities and D2H of forces + per-atom arrays inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mbpol_2b3b_trimers_per_s"
+UNIT = "trimers/s"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# host-side helpers shared with the CPU tests (tests/test_shard.py)
+# ------------------------------------------------------------------------------------------------------------
+def shard_range(total, rank, nranks):
+    """Contiguous shard [lo, hi) of a work list -- identical to the rule inside mbpol_b200_compute."""
+    return total * rank // nranks, total * (rank + 1) // nranks
+
+
+def pack_outputs(out, mxatms):
+    """Host mirror of the packed device buffer layout (include/mbpol_b200.h): per-atom arrays then 32 scalars."""
+    n = mxatms
+    buf = np.zeros(22 * n + 32)
+    buf[0:n], buf[n:2 * n], buf[2 * n:3 * n] = out["fxx"], out["fyy"], out["fzz"]
+    buf[3 * n:4 * n] = out["atomic_energy"]
+    if out.get("atomic_stress") is not None:
+        buf[4 * n:13 * n] = out["atomic_stress"]
+    if out.get("atomic_fdecomp") is not None:
+        buf[13 * n:22 * n] = out["atomic_fdecomp"]
+    s = buf[22 * n:]
+    s[0], s[1], s[2], s[3] = out["eng2"], out["vir2"], out["eng3"], out["vir3"]
+    s[4:13] = out["stress"]
+    return buf
+
+
+def allreduce_packed(t):
+    """The single collective of a multi-GPU step: sum the packed per-rank partial outputs in place."""
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class DeviceArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        load = [s for s in sm if mx and s > 0.5 * mx[0]] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU evaluators (oracle/_ref) under the restated list-driven driver
+# ------------------------------------------------------------------------------------------------------------
+def reference_sample(box, threads, n_trimers_sample):
+    """One bounded CPU step: S trimers plus the proportional number of dimers.  Returns (seconds, trimers, info)."""
+    from oracle.oracle import Oracle
+    o = Oracle()
+    kind = "reference" if o.have_reference else "port"
+    out = o.forces(box, mode="listed", use_ref=o.have_reference, nthreads=threads, want_stress=False, want_fdecomp=True,
+                   want_lists=False, max_clusters=n_trimers_sample)
+    nt, nd = out["ntrimer"], out["ndimer"]
+    st, sd = min(nt, n_trimers_sample), min(nd, n_trimers_sample)
+    t3, t2 = out["timing"]["t3b_s"], out["timing"]["t2b_s"]
+    # a proportional step evaluates st trimers and st*nd/nt dimers
+    t_step = t3 + t2 * (st * nd / max(nt, 1)) / max(sd, 1)
+    info = {"kind": kind, "flags": o.ref_flags() or "restated evaluators, g++ -O2 -ffp-contract=off",
+            "us_per_trimer_per_thread": 1e6 * t3 * threads / max(st, 1), "us_per_dimer_per_thread": 1e6 * t2 * threads / max(sd, 1),
+            "list_s_excluded": out["timing"]["list_s"], "n_dimers": nd, "n_trimers": nt}
+    return t_step, st, info
+
+
+def run_reference(args, box, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or 4000 * threads
+    vals = []
+    info = {}
+    for it in range(args.warmup + args.steps):
+        t, st, info = reference_sample(box, threads, sample)
+        if it >= args.warmup:
+            vals.append((t, st))
+    tsum = sum(v[0] for v in vals)
+    tri = sum(v[1] for v in vals)
+    value = tri / tsum
+    sample_txt = "%d trimers + proportional dimers of the %d-H2O box per step (lists excluded)" % (vals[0][1], box["nw"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * info["n_trimers"] / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(box, args, info["n_dimers"], info["n_trimers"]),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": info["kind"], "sample": sample_txt,
+                             "flags": info["flags"], "us_per_trimer_per_thread": info["us_per_trimer_per_thread"],
+                             "us_per_dimer_per_thread": info["us_per_dimer_per_thread"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "ms_per_step is the full-box step extrapolated from the bounded sample; the reference's own O(N^3) "
+                    "enumeration (mbpol.f90:306-374) is NOT included -- the evaluators are driven from a neighbour list"}
+    print(json.dumps(line))
+
+
+def workload_config(box, args, nd, nt):
+    return {"workload": "%d H2O MB-pol box (cubic, L=%.2f A, seed %d): 2B+3B energies, forces, per-atom energy and "
+                        "force-decomposition tensor, heat-flux contractions" % (box["nw"], box["L"], box["seed"]),
+            "n_waters": box["nw"], "n_dimers": int(nd), "n_trimers": int(nt), "flags": args.flags,
+            "parallelism": "work-list shards x%d, replicated coordinates, one all-reduce" % args.gpus,
+            "l2": "flushed between timed steps (256 MiB memset)"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nw", type=int, default=32768, help="waters in the synthetic box (BASELINE configs: 4096, 32768)")
+    ap.add_argument("--flags", type=int, default=3, help="1 atomic energy | 2 force decomposition | 4 atomic stress (HEAT_STRESS)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trimers per CPU-baseline sample (default 4000 per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import mbpol_b200 as mb
+    from mbpol_b200 import synth
+    box = synth.make_water_box(args.nw)
+
+    if args.impl == "reference":
+        run_reference(args, box, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = box["mxatms"]
+    h = mb.mbpol_init(box["nttm2"], flags=args.flags, device=local)
+    mb.mbpol_set_shard(h, rank, world)
+    stream = torch.cuda.ExternalStream(mb.mbpol_stream(h), device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    vel = (box["vxx"], box["vyy"], box["vzz"])
+    want_s = bool(args.flags & 4)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    mb.mbpol_upload(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"], *vel)
+    mb.mbpol_compute(h)
+    ptr, cnt = mb.mbpol_device_outputs(h)
+    packed = torch.as_tensor(DeviceArray(ptr, cnt), device="cuda")
+    counts = mb.mbpol_counts(h)
+    k3 = []
+
+    def step():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0.record(stream)
+            mb.mbpol_compute(h)
+            if world > 1:
+                allreduce_packed(packed)
+            e1.record(stream)
+        e1.synchronize()
+        k3.append(mb.mbpol_kernel_times(h))
+        return e0.elapsed_time(e1)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    k3.clear()
+    ms = [step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = torch.tensor([sum(ms) / len(ms)], dtype=torch.float64, device="cuda")
+    t3 = torch.tensor([np.mean([k["k3b_ms"] for k in k3])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    ms_step = float(t_dev.item())
+    launches = int(k3[-1]["launches"]) * args.steps
+
+    # ---- end-to-end through the public call (host buffers, copies inside the timed region) ------------------
+    outs = {k: np.zeros(n) for k in ("fxx", "fyy", "fzz", "ae")}
+    afd = np.zeros(9 * n) if args.flags & 2 else None
+    ast = np.zeros(9 * n) if want_s else None
+    stress = np.zeros(9)
+
+    def e2e_step():
+        t0 = time.perf_counter()
+        if world > 1:
+            mb.mbpol_upload(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"], *vel)
+            mb.mbpol_compute(h)
+            with torch.cuda.stream(stream):
+                allreduce_packed(packed)
+            stream.synchronize()
+            r = mb.mbpol_download(h, outs["fxx"], outs["fyy"], outs["fzz"], stress=stress, atomic_energy=outs["ae"],
+                                  atomic_stress=ast, atomic_fdecomp=afd)
+        else:
+            r = mb.mbpol_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"],
+                                outs["fxx"], outs["fyy"], outs["fzz"], stress=stress, atomic_energy=outs["ae"], atomic_stress=ast,
+                                atomic_fdecomp=afd, vxx=vel[0], vyy=vel[1], vzz=vel[2])
+        return time.perf_counter() - t0, r
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    te = []
+    for _ in range(args.steps):
+        dt, res = e2e_step()
+        te.append(dt)
+    barrier()
+    t_e2e = torch.tensor([float(np.mean(te))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    h2d = 8 * n * 6 + 4 * box["nttm2"]
+    d2h = 8 * (n * (4 + (9 if afd is not None else 0) + (9 if ast is not None else 0)) + 32)
+
+    if rank == 0:
+        nt, nd = counts["trimers"], counts["dimers"]
+        peak = mb.measure_fp64_peak()
+        k3ms = float(t3.item())
+        nts = counts["trimers_shard"]
+        achieved = nts * mb.FLOP_PER_TRIMER / (k3ms * 1e-3) * 1e-12
+        step_flops = (nd * mb.FLOP_PER_DIMER + nt * mb.FLOP_PER_TRIMER)
+        line = {"metric": METRIC, "value": nt / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(box, args, nd, nt),
+                "e2e": {"value": nt / float(t_e2e.item()), "unit": UNIT, "ms_per_step": 1e3 * float(t_e2e.item()),
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp64", "kernel": "k_trimers", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "traffic": None, "kernel_ms": k3ms,
+                             "peak_source": "measured live: independent DFMA chains (mbpol_b200_measure_fp64_peak); "
+                                            "MEASURED_PEAKS.json has no FP64 entry",
+                             "algorithmic_flop_per_trimer": mb.FLOP_PER_TRIMER,
+                             "step_frac": step_flops / (ms_step * 1e-3) * 1e-12 / peak / world},
+                "phases_ms": {k: float(np.mean([q[k] for q in k3])) for k in ("lists_ms", "k2b_ms", "k3b_ms", "total_ms")},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            t, st, info = reference_sample(box, threads, args.cpu_sample or 2000 * threads)
+            line["cpu_baseline"] = {"value": st / t, "unit": UNIT, "cores": threads, "kind": info["kind"],
+                                    "sample": "%d trimers + proportional dimers of the same box, lists excluded" % st,
+                                    "flags": info["flags"], "us_per_trimer_per_thread": info["us_per_trimer_per_thread"],
+                                    "us_per_dimer_per_thread": info["us_per_dimer_per_thread"]}
+        # sanity: the summed energies of the e2e call (host accumulate semantics) stay finite
+        line["check"] = {"eng2": res["eng2"], "eng3": res["eng3"]}
+        print(json.dumps(line))
+    mb.mbpol_fini(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,15 @@ def mbpol_kernel_times(h):
     return {"lists_ms": ms[0], "k2b_ms": ms[1], "k3b_ms": ms[2], "total_ms": ms[3], "launches": n.value}
 
 
+def measure_fp64_peak():
+    """Measured DFMA throughput of the current GPU in TFLOP/s (2 flop per DFMA)."""
+    t, ms = C.c_double(), C.c_double()
+    rc = load_library().mbpol_b200_measure_fp64_peak(C.byref(t), C.byref(ms))
+    if rc:
+        raise MBPolError("mbpol_b200_measure_fp64_peak failed with status %d" % rc)
+    return t.value
+
+
 def mbpol_eval_dimers(w, want_fm=True):
     """Batched mbpol_2b_poly_: w [n,18] imaged coordinates -> E[n], g[n,18], fm[n,6,6,3] (kcal/mol)."""
     w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 18)

@@ -515,6 +515,26 @@ __global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// FP64 roofline probe: 8 independent register-resident DFMA chains per thread (the denominator bench.py quotes)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b)
+{
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // =========================================================================================================
 // host side
 // =========================================================================================================
@@ -904,6 +924,32 @@ int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches
     if (!h) return MBPOL_B200_EINVAL;
     if (ms) std::copy(h->ms, h->ms + 4, ms);
     if (launches) *launches = h->launches;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_measure_fp64_peak(double* tflops, double* ms_out)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return MBPOL_B200_ENODEVICE;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * sms * 8 * 256) != cudaSuccess) return MBPOL_B200_ECUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 20000;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<sms * 8, 256>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return MBPOL_B200_ECUDA;
+    *tflops = 2.0 * 64.0 * iters * (double)sms * 8 * 256 / (best * 1e-3) * 1e-12;
+    if (ms_out) *ms_out = best;
     return MBPOL_B200_OK;
 }
 

@@ -99,6 +99,10 @@ int mbpol_b200_get_lists(mbpol_b200_handle* handle, int* dimers /*2*n*/, long lo
                          int* trimers /*3*n*/, long long trimer_cap);   /* 0-based water indices, i<j(<k), full lists */
 int mbpol_b200_kernel_times(mbpol_b200_handle* handle, float* ms /*[4]: lists, 2B, 3B, total*/, long long* launches);
 
+/* FP64 roofline probe: best-of-3 throughput of independent register-resident DFMA chains on the current device
+ * (2 flop per DFMA), the measured denominator for the "fraction of FP64 FMA peak" figures. */
+int mbpol_b200_measure_fp64_peak(double* tflops, double* ms);
+
 /* Batched per-cluster evaluation: n clusters, coordinates already imaged as the reference's do_dimer/do_trimer
  * pass them (mbpol.f90:505-517, 875-894).  w: [n][18] or [n][27] (O,H,H per water); outputs in kcal/mol:
  * E[n], g: [n][18|27], fm: [n][108|243] or NULL (diagonal blocks are written as 0; the reference leaves them

@@ -1,0 +1,55 @@
+"""CPU test of OUR polynomial evaluation schedule (tools/gen_poly.py): the generated straight-line body, compiled
+as plain C++, must reproduce the table-driven oracle polynomial and its gradient."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HARNESS = r"""
+#define PFMA(a,b,c) ((a)*(b)+(c))
+#define PMUL(a,b) ((a)*(b))
+#define PADD(a,b) ((a)+(b))
+#define PCOEF(k) a[k]
+extern "C" double sched2b(const double* a, const double* x, double* g) { double E;
+#include "poly2b_body.inc"
+return E; }
+extern "C" double sched3b(const double* a, const double* x, double* g) { double E;
+#include "poly3b_body.inc"
+return E; }
+"""
+
+
+def test_generated_schedule_matches_tables(tmp_path, oracle):
+    gen = tmp_path / "gen"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_poly.py"), "--outdir", str(gen),
+                           "--parts2b", "3", "--parts3b", "5"])
+    # structural checks on the PTX parts: every part is a .func taking (buf, nbatch) and all FP64 ops are accounted for
+    hdr = open(gen / "poly_gen.h").read()
+    n3 = int(hdr.split("POLY3B_FP64_INSTR")[1].split()[0])
+    ptx_ops = 0
+    for k in range(5):
+        txt = open(gen / ("poly3b_part%d.ptx" % k)).read()
+        assert ".visible .func poly3b_part%d" % k in txt and ".target sm_100a" in txt
+        ptx_ops += sum(txt.count(m) for m in ("fma.rn.f64", "mul.rn.f64", "add.rn.f64"))
+    assert ptx_ops == n3 and n3 < 111818 // 1.5        # fewer FP64 instructions than the reference has flops
+    src = tmp_path / "h.cpp"
+    src.write_text(HARNESS)
+    lib = tmp_path / "libsched.so"
+    subprocess.check_call(["g++", "-O0", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(gen), str(src), "-o", str(lib)])
+    L = C.CDLL(str(lib))
+    rng = np.random.default_rng(3)
+    dp = C.POINTER(C.c_double)
+    for tag, nv, f in (("2b", 31, L.sched2b), ("3b", 36, L.sched3b)):
+        f.restype = C.c_double
+        for trial in range(3):
+            a = oracle.coef(tag) if trial == 0 else rng.normal(size=len(oracle.coef(tag)))
+            x = rng.uniform(0.05, 1.3, size=nv)
+            g = np.zeros(nv)
+            E = f(a.ctypes.data_as(dp), x.ctypes.data_as(dp), g.ctypes.data_as(dp))
+            Er, gr = oracle.poly(tag, a, x)
+            assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+            assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()

@@ -1,0 +1,213 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracle on
+the same seeded inputs, against the committed golden fixtures, and -- at BASELINE sizes -- through size-independent
+properties.  Tolerances are the north_star's: 1e-10 relative on total 2B+3B energy, 1e-9 relative RMS on forces and
+per-atom tensors, bit-exact dimer/trimer list membership."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_rms, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-10
+F_TOL = 1e-9
+OFF6 = ~np.eye(6, dtype=bool)
+OFF9 = ~np.eye(9, dtype=bool)
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import mbpol_b200
+    mbpol_b200.load_library()
+    return mbpol_b200
+
+
+def test_legacy_symbols_known_answers(mb):
+    """mbpol_2b_poly_ / mbpol_3b_poly_ (the reference's own C symbols) on SURVEY.md Appendix A."""
+    kat = json.load(open(os.path.join(GOLDEN, "kat_appendix_a.json")))
+    E, g1, g2, fm = mb.mbpol_2b_poly(kat["w1"], kat["w2"])
+    assert abs(E - 5.361320870419604) <= E_TOL * abs(E)
+    np.testing.assert_allclose(np.r_[g1, g2], np.r_[kat["2b"]["g1"], kat["2b"]["g2"]], atol=F_TOL * 18)
+    np.testing.assert_allclose(fm[OFF6], np.array(kat["2b"]["fm"])[OFF6], atol=F_TOL * 18)
+    E, g1, g2, g3, fm = mb.mbpol_3b_poly(kat["w1"], kat["w2"], kat["w3"])
+    assert abs(E - (-0.37951111966318934)) <= E_TOL * abs(E)
+    np.testing.assert_allclose(np.r_[g1, g2, g3], np.r_[kat["3b"]["g1"], kat["3b"]["g2"], kat["3b"]["g3"]], atol=F_TOL)
+    np.testing.assert_allclose(fm[OFF9], np.array(kat["3b"]["fm"])[OFF9], atol=F_TOL)
+    r = mb.mbpol_cutoffs()
+    assert r == (6.5, 4.5)
+
+
+def test_golden_clusters_batched(mb, golden_clusters):
+    c = golden_clusters
+    E, g, fm = mb.mbpol_eval_dimers(c["dimer_w"])
+    scale = np.maximum(np.abs(c["dimer_E"]), np.abs(c["dimer_g"]).max(1))
+    assert np.all(np.abs(E - c["dimer_E"]) <= E_TOL * scale)
+    assert np.all(np.abs(g - c["dimer_g"]).max(1) <= F_TOL * scale)
+    assert np.abs(fm - c["dimer_fm"])[:, OFF6].max() <= F_TOL * np.abs(c["dimer_fm"][:, OFF6]).max()
+    E, g, fm = mb.mbpol_eval_trimers(c["trimer_w"])
+    scale = np.maximum(np.abs(c["trimer_E"]), np.abs(c["trimer_g"]).max(1))
+    assert np.all(np.abs(E - c["trimer_E"]) <= E_TOL * scale)
+    assert np.all(np.abs(g - c["trimer_g"]).max(1) <= F_TOL * scale)
+    assert np.abs(fm - c["trimer_fm"])[:, OFF9].max() <= F_TOL * np.abs(c["trimer_fm"][:, OFF9]).max()
+
+
+def compare(out, ref, keys):
+    e, er = out["eng2"] + out["eng3"], ref["eng2"] + ref["eng3"]
+    assert abs(e - er) <= E_TOL * abs(er)
+    for k in ("eng2", "vir2", "eng3", "vir3"):
+        assert abs(out[k] - ref[k]) <= 1e-9 * abs(ref[k]), k
+    for k in keys:
+        assert rel_rms(out[k], ref[k]) <= F_TOL, k
+
+
+def test_box64_against_golden_faithful_reference(mb, box64, golden_box64):
+    """64-water box vs the reference evaluators in the reference's own enumeration order (golden fixture)."""
+    h = mb.mbpol_init(box64["nttm2"], flags=7)
+    out = mb.run_box(h, box64, want_stress=True)
+    d, t = mb.mbpol_lists(h)
+    mb.mbpol_fini(h)
+    g = golden_box64
+    assert np.array_equal(sort_rows(d), sort_rows(g["dimers"]))
+    assert np.array_equal(sort_rows(t), sort_rows(g["trimers"]))
+    ref = {k: g[k] for k in ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress")}
+    ref.update(dict(zip(("eng2", "vir2", "eng3", "vir3"), g["scalars"])))
+    compare(out, ref, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress"))
+
+
+@pytest.mark.parametrize("nw", [27, 256, 700])
+def test_box_against_oracle(mb, oracle, synth, nw):
+    box = synth.make_water_box(nw, seed=11 + nw)
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    out = mb.run_box(h, box, want_stress=True)
+    d, t = mb.mbpol_lists(h)
+    c = mb.mbpol_counts(h)
+    mb.mbpol_fini(h)
+    ref = oracle.forces(box, mode="listed", use_ref=oracle.have_reference, nthreads=os.cpu_count())
+    assert c["dimers"] == ref["ndimer"] and c["trimers"] == ref["ntrimer"]
+    assert np.array_equal(sort_rows(d), sort_rows(ref["dimers"]))
+    assert np.array_equal(sort_rows(t), sort_rows(ref["trimers"]))
+    compare(out, ref, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress"))
+    n = box["mxatms"]
+    j1, j2 = oracle.heat_flux(n, ref["atomic_energy"], ref["atomic_stress"], box["vxx"], box["vyy"], box["vzz"])
+    j3 = oracle.heat_flux2_fdecomp(n, ref["atomic_fdecomp"], box["vxx"], box["vyy"], box["vzz"])
+    jr = np.r_[j1, j2, j3]
+    assert np.abs(out["jflux"] - jr).max() <= F_TOL * np.abs(jr).max()
+
+
+def test_default_flags_leave_atomic_stress_alone(mb, box64, oracle):
+    """Reference default build: HEAT_STRESS off -> atomic_stress_mbpol stays zero."""
+    h = mb.mbpol_init(box64["nttm2"])            # DEFAULT_FLAGS = energy + force decomposition
+    out = mb.run_box(h, box64, want_stress=False)
+    with pytest.raises(mb.MBPolError):
+        mb.run_box(h, box64, want_stress=True)     # asking for it without the flag is an error, not garbage
+    mb.mbpol_fini(h)
+    ref = oracle.forces(box64, mode="listed", use_ref=oracle.have_reference, want_stress=False)
+    compare(out, ref, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_fdecomp"))
+
+
+def test_accumulate_semantics(mb, box64):
+    """Outputs are added into the caller's arrays (fxx = fxx - g, stress = stress + strs, mbpol.f90:247-255, 582-599)."""
+    h = mb.mbpol_init(box64["nttm2"])
+    a = mb.run_box(h, box64)
+    n = box64["mxatms"]
+    fx, fy, fz = np.full(n, 1.5), np.full(n, -2.0), np.zeros(n)
+    st = np.arange(9.0)
+    r = mb.mbpol_forces(h, box64["imcon"], box64["cell"], box64["nttm2"], box64["listttm2"], box64["xxx"], box64["yyy"],
+                        box64["zzz"], fx, fy, fz, engsrp=10.0, virsrp=-3.0, stress=st)
+    mb.mbpol_fini(h)
+    assert rel_rms(fx - 1.5, a["fxx"]) < 1e-11 and rel_rms(fy + 2.0, a["fyy"]) < 1e-11
+    assert rel_rms(st - np.arange(9.0), a["stress"]) < 1e-11
+    assert abs(r["engsrp"] - 10.0 - (a["eng2"] + a["eng3"])) < 1e-9 * abs(a["eng2"])
+
+
+def test_cell_types(mb, synth):
+    """imcon 1/2/3 (mbpol.f90:1319-1358) on the same cubic cell give the same lists and energies; imcon 0 is rejected."""
+    box = synth.make_water_box(216, seed=3)
+    res = []
+    for imcon in (1, 2, 3):
+        b = dict(box); b["imcon"] = imcon
+        h = mb.mbpol_init(b["nttm2"])
+        out = mb.run_box(h, b)
+        res.append((out, sort_rows(mb.mbpol_lists(h)[1])))
+        mb.mbpol_fini(h)
+    for out, tl in res[1:]:
+        assert np.array_equal(tl, res[0][1])
+        assert abs(out["eng3"] - res[0][0]["eng3"]) <= 1e-10 * abs(res[0][0]["eng3"])
+        assert rel_rms(out["fxx"], res[0][0]["fxx"]) <= F_TOL
+    b = dict(box); b["imcon"] = 0
+    h = mb.mbpol_init(b["nttm2"])
+    with pytest.raises(mb.MBPolError):
+        mb.run_box(h, b)
+    mb.mbpol_fini(h)
+
+
+def test_shards_sum_to_the_whole(mb, synth):
+    """(rank, nranks) shards of the work lists add up to the single-rank result -- what gdsum / NCCL completes."""
+    box = synth.make_water_box(256)
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    full = mb.run_box(h, box, want_stress=True)
+    acc = None
+    ntri = 0
+    for r in range(3):
+        mb.mbpol_set_shard(h, r, 3)
+        p = mb.run_box(h, box, want_stress=True)
+        ntri += mb.mbpol_counts(h)["trimers_shard"]
+        if acc is None:
+            acc = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.items()}
+        else:
+            for k, v in p.items():
+                acc[k] = acc[k] + v
+    assert ntri == mb.mbpol_counts(h)["trimers"]
+    mb.mbpol_fini(h)
+    compare(acc, full, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress", "jflux"))
+
+
+def test_full_size_properties_4096(mb, oracle, synth):
+    """BASELINE config 2 (4096 H2O): size-independent properties + sampled clusters against the oracle."""
+    box = synth.make_water_box(4096)
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    out = mb.run_box(h, box, want_stress=True)
+    d, t = mb.mbpol_lists(h)
+    assert len(np.unique(t, axis=0)) == len(t) and np.all(t[:, 0] < t[:, 1]) and np.all(t[:, 1] < t[:, 2])
+    assert len(np.unique(d, axis=0)) == len(d) and np.all(d[:, 0] < d[:, 1])
+    e = out["eng2"] + out["eng3"]
+    assert abs(out["atomic_energy"].sum() - e) <= 1e-10 * abs(e)                     # sum_i e_i = E
+    for k in ("fxx", "fyy", "fzz"):
+        assert abs(out[k].sum()) <= 1e-9 * np.abs(out[k]).sum()                       # no net force
+        assert not np.any(out[k][3 * 4096:])                                          # M-sites untouched
+    assert np.allclose(out["stress"].reshape(3, 3), out["stress"].reshape(3, 3).T, rtol=0, atol=1e-9 * np.abs(out["stress"]).max())
+    assert abs(np.trace(out["stress"].reshape(3, 3)) + (out["vir2"] + out["vir3"])) <= 1e-9 * abs(out["vir2"])   # tr(stress) = -virial
+    # rigid translation (re-wrapped) + relabelling of the waters leave the physics unchanged
+    L = box["L"]
+    perm = np.random.default_rng(0).permutation(4096)
+    b = dict(box)
+    for k, s in (("xxx", 0.4 * L), ("yyy", -1.3), ("zzz", 7.7)):
+        v = box[k][:3 * 4096].reshape(4096, 3)[perm].ravel() + s
+        b[k] = np.concatenate([v - L * np.round(v / L), box[k][3 * 4096:]])
+    for k in ("vxx", "vyy", "vzz"):
+        b[k] = np.concatenate([box[k][:3 * 4096].reshape(4096, 3)[perm].ravel(), box[k][3 * 4096:]])
+    out2 = mb.run_box(h, b, want_stress=True)
+    assert mb.mbpol_counts(h)["trimers"] == len(t)
+    assert abs((out2["eng2"] + out2["eng3"]) - e) <= 1e-9 * abs(e)
+    f1 = out["fxx"][:3 * 4096].reshape(4096, 3)[perm].ravel()
+    assert rel_rms(out2["fxx"][:3 * 4096], f1) <= F_TOL
+    assert np.abs(out2["jflux"][:6] - out["jflux"][:6]).max() <= 1e-8 * np.abs(out["jflux"][:6]).max()
+    mb.mbpol_fini(h)
+    # sampled clusters of the full-size lists against the oracle evaluators
+    nw = 4096
+    mono = np.stack([box["xxx"][:3 * nw], box["yyy"][:3 * nw], box["zzz"][:3 * nw]], 1).reshape(nw, 3, 3)
+    mono[:, 1:] = mono[:, :1] + (mono[:, 1:] - mono[:, :1]) - L * np.round((mono[:, 1:] - mono[:, :1]) / L)
+    sel = t[np.random.default_rng(1).choice(len(t), 64, replace=False)]
+
+    def near(wa, wb):
+        dd = wa[0] - wb[0]
+        return wa - wa[0] + wb[0] + (dd - L * np.round(dd / L))
+    w = np.array([np.r_[near(mono[i], mono[j]).ravel(), mono[j].ravel(), near(mono[k], mono[j]).ravel()] for i, j, k in sel])
+    E, g, _ = mb.mbpol_eval_trimers(w, want_fm=False)
+    for q in range(len(sel)):
+        ref = oracle.trimer(w[q, :9], w[q, 9:18], w[q, 18:], ref=oracle.have_reference)
+        sc = max(abs(ref[0]), np.abs(np.r_[ref[1], ref[2], ref[3]]).max())
+        assert abs(E[q] - ref[0]) <= E_TOL * sc and np.abs(g[q] - np.r_[ref[1], ref[2], ref[3]]).max() <= F_TOL * sc
