@@ -108,6 +108,16 @@ __global__ void k_cell_fill(int nw, const int* __restrict__ cell_id, const int* 
 //   nb3[i][*]: j != i with sqrt(r^2) <= r3f (reject: r .gt. r3f,      mbpol.f90:865-869)
 // d = O_min(i,j) - O_max(i,j), then the reference's minimum image.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sort_row(int* __restrict__ row, int n)
+{
+    for (int a = 1; a < n; ++a) {
+        const int v = row[a];
+        int b = a - 1;
+        while (b >= 0 && row[b] > v) { row[b + 1] = row[b]; --b; }
+        row[b + 1] = v;
+    }
+}
+
 __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C, Grid G, const int* __restrict__ cell_start,
                              const int* __restrict__ sorted, int* __restrict__ nb2, int* __restrict__ n2, int* __restrict__ nb3,
                              int* __restrict__ n3, int* __restrict__ overflow)
@@ -151,8 +161,14 @@ __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C
                 }
             }
     if (c2 > NB2_CAP || c3 > NB3_CAP) atomicExch(overflow, 1);
-    n2[i] = min(c2, NB2_CAP);
-    n3[i] = min(c3, NB3_CAP);
+    c2 = min(c2, NB2_CAP);
+    c3 = min(c3, NB3_CAP);
+    n2[i] = c2;
+    n3[i] = c3;
+    // The cell fill order comes from atomics; sort the rows so that the lists (and therefore the per-rank shards cut
+    // out of them) are identical on every GPU and from call to call.
+    sort_row(nb2 + (size_t)i * NB2_CAP, c2);
+    sort_row(nb3 + (size_t)i * NB3_CAP, c3);
 }
 
 __global__ void k_fill_dimers(int nw, const int* __restrict__ nb2, const int* __restrict__ n2, const long long* __restrict__ off,
