@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "gen/poly_gen.h"
+#include "mbpol_tape.cuh"
 
 // linear coefficients: referenced by name from the generated PTX (.extern .const)
 extern __constant__ double mbpol_coef2b[1153];
@@ -76,6 +77,15 @@ __device__ __forceinline__ double switch_fn(double r, double ri, double rf, doub
     return 1.0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// polynomial front-ends.  ENGINE 0: generated straight-line PTX parts (tools/gen_poly.py), per-thread record in
+// local memory.  ENGINE 1: coefficient-tape interpreter (tools/gen_tape.py, mbpol_tape.cuh); needs the whole CTA.
+// ---------------------------------------------------------------------------------------------------------
+struct PolyCtx {
+    void* smem;              // TapeSmem<NV>* for ENGINE 1
+    const double* tape;      // device tape for ENGINE 1
+};
+
 // =========================================================================================================
 // 3B
 // =========================================================================================================
@@ -87,9 +97,11 @@ __device__ constexpr int V3K[36] = {0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2,
 // r[27]: imaged coordinates (any common origin).  Outputs in kcal/mol:
 //   E, cv[n] with  dE/dr_a += cv[n]*(r_a - r_b),  dE/dr_b -= ...   for variable n = (a,b); the three switch-gradient
 //   terms (mbpol-3b-poly.cpp:292-309) are folded into cv[33..35] because they act along the same O-O vectors.
-__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36])
+template <int ENGINE>
+__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
 {
-    double rec[POLY3B_RECORD_DOUBLES];
+    double xv[ENGINE ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE ? 36 : 1];
+    double* gp = ENGINE ? gp_ : xv + 37;      // ENGINE 0: x and g live in the per-thread record (local memory)
     double rinv[36];
 #pragma unroll
     for (int n = 0; n < 36; ++n) {
@@ -97,10 +109,16 @@ __device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, do
         const double dx = r[a] - r[b], dy = r[a + 1] - r[b + 1], dz = r[a + 2] - r[b + 2];
         const double d = sqrt(dx * dx + dy * dy + dz * dz);
         rinv[n] = 1.0 / d;
-        rec[n] = exp(-mbpol_par.k3[V3K[n]] * (d - mbpol_par.d3[V3K[n]]));
+        xv[n] = exp(-mbpol_par.k3[V3K[n]] * (d - mbpol_par.d3[V3K[n]]));
     }
-    POLY3B_CALL_ALL(rec, 1u);
-    const double Epoly = rec[36];
+    double Epoly;
+    if (ENGINE == 0) {
+        POLY3B_CALL_ALL(xv, 1u);
+        Epoly = xv[36];
+    } else {
+        tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
+                         *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    }
     // switch on the three O-O distances: rinv[33..35] = 1/|Oa-Ob|, 1/|Oa-Oc|, 1/|Ob-Oc|
     const double drab = 1.0 / rinv[33], drac = 1.0 / rinv[34], drbc = 1.0 / rinv[35];
     double gab, gac, gbc;
@@ -110,7 +128,7 @@ __device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, do
     const double s = sab * sac + sab * sbc + sac * sbc;
 #pragma unroll
     for (int n = 0; n < 36; ++n)
-        cv[n] = -mbpol_par.k3[V3K[n]] * (rec[37 + n] * s) * rec[n] * rinv[n];
+        cv[n] = -mbpol_par.k3[V3K[n]] * (gp[n] * s) * xv[n] * rinv[n];
     cv[33] += gab * (sac + sbc) * Epoly * rinv[33];
     cv[34] += gac * (sab + sbc) * Epoly * rinv[34];
     cv[35] += gbc * (sab + sac) * Epoly * rinv[35];
@@ -182,7 +200,8 @@ __device__ __forceinline__ void lonepair_spread(const double* ohh, const double*
 // w[18]: imaged O,H,H of water a then water b (any common origin).  Outputs in kcal/mol: E, g[18];
 // fm (optional, 108 doubles, index 18*i+3*j+c) = the reference's folded pair force matrix with zero diagonal blocks.
 // Returns false (E = 0, g = 0) when rOO > r2f, like the reference's early return (mbpol-2b-poly.cpp:370-371).
-__device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, double* fm)
+template <int ENGINE>
+__device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, double* fm, const PolyCtx& ctx)
 {
     double xc[30];
 #pragma unroll
@@ -194,11 +213,13 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     for (int i = 0; i < 18; ++i) g[i] = 0.0;
     if (fm)
         for (int i = 0; i < 108; ++i) fm[i] = 0.0;
-    if (rOO > mbpol_par.r2f) return false;
+    const bool inside = !(rOO > mbpol_par.r2f);
+    if (ENGINE == 0 && !inside) return false;           // the tape engine has CTA barriers: every thread walks on
     lonepair_sites(xc + 0, xc + 18, xc + 21);
     lonepair_sites(xc + 9, xc + 24, xc + 27);
 
-    double rec[POLY2B_RECORD_DOUBLES];
+    double xv[ENGINE ? 31 : POLY2B_RECORD_DOUBLES], gp_[ENGINE ? 31 : 1];
+    double* gp = ENGINE ? gp_ : xv + 32;
     double gfac[31];    // dv/dr / r : the variable's gradient is gfac * (r_a - r_b)
 #pragma unroll
     for (int n = 0; n < 31; ++n) {
@@ -211,15 +232,22 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
         const double ri = 1.0 / rr;
         if (V2K[n] >= 2 && V2K[n] <= 4) {   // "coulomb" type: exp(k(r0-r))/r
             const double val = e1 * ri;
-            rec[n] = val;
+            xv[n] = val;
             gfac[n] = -(k + ri) * val * ri;
         } else {
-            rec[n] = e1;
+            xv[n] = e1;
             gfac[n] = -k * e1 * ri;
         }
     }
-    POLY2B_CALL_ALL(rec, 1u);
-    const double Epoly = rec[31];
+    double Epoly;
+    if (ENGINE == 0) {
+        POLY2B_CALL_ALL(xv, 1u);
+        Epoly = xv[31];
+    } else {
+        tape_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,
+                         *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
+    }
+    if (!inside) return false;
 
     double xg[30];
 #pragma unroll
@@ -230,7 +258,7 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
 #pragma unroll
     for (int n = 0; n < 31; ++n) {
         const int a = V2A[n], b = V2B[n];
-        const double c = rec[32 + n] * gfac[n];
+        const double c = gp[n] * gfac[n];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const double d = c * (xc[3 * a + i] - xc[3 * b + i]);

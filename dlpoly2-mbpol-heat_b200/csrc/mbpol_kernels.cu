@@ -23,10 +23,15 @@
 #include "mbpol_b200.h"
 #include "mbpol_device.cuh"
 #include "gen/mbpol_model_data.h"
+#include <cstdlib>
 
 __constant__ double mbpol_coef2b[1153];
 __constant__ double mbpol_coef3b[1163];
 __constant__ MbpolParams mbpol_par;
+__constant__ unsigned c_tape_ops2b[TAPE2B_NOPS];
+__constant__ unsigned c_tape_ops3b[TAPE3B_NOPS];
+__constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][2];
+__constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][2];
 
 namespace {
 
@@ -261,13 +266,19 @@ __device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, cons
 // ---------------------------------------------------------------------------------------------------------
 // K3: trimers.  One thread per accepted trimer of this shard.
 // ---------------------------------------------------------------------------------------------------------
+template <int ENGINE>
 __global__ void __launch_bounds__(256, 1)
 k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
+          const double* __restrict__ tape)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const PolyCtx ctx{dyn_smem, tape};
+    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t0_ < ntri;
+    const long long t = valid ? t0_ : ntri - 1;          // idle lanes shadow the last trimer (tape engine: CTA barriers)
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
-    if (t < ntri) {
+    if (ENGINE == 1 || valid) {
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
         double r[27];
         // imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
@@ -296,11 +307,12 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
             r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
         }
         double E, cv[36];
-        trimer_eval(r, E, cv);
+        trimer_eval<ENGINE>(r, E, cv, ctx);
         double g[27];
         trimer_gradient(r, cv, g);
         const double eu = MBPOL_ENGUNIT;
         const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
+        if (valid) {
         sc[0] = E * eu;
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
@@ -358,6 +370,7 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
                 atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
             }
         }
+        }   // valid
     }
     // scalars: eng3, vir3, stress (symmetric fill: 2,3,4 / 3?,...)  -> scal[S_ENG3], scal[S_VIR3], scal[S_STRESS+..]
     double v2[2] = {sc[0], sc[1]};
@@ -370,13 +383,19 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
 // ---------------------------------------------------------------------------------------------------------
 // K2: dimers
 // ---------------------------------------------------------------------------------------------------------
+template <int ENGINE>
 __global__ void __launch_bounds__(256, 1)
 k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-         const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+         const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
+         const double* __restrict__ tape)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const PolyCtx ctx{dyn_smem, tape};
+    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t0_ < ndim;
+    const long long t = valid ? t0_ : ndim - 1;
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (t < ndim) {
+    if (ENGINE == 1 || valid) {
         const int mi = dim[t].x, mj = dim[t].y;
         double wi[9], wj[9], w[18];
 #pragma unroll
@@ -399,9 +418,10 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
         double E, g[18];
         double fm[108];
         const bool want_s = (flags & MBPOL_B200_WANT_ATOMIC_STRESS) != 0;
-        dimer_eval(w, E, g, want_s ? fm : nullptr);
+        dimer_eval<ENGINE>(w, E, g, want_s ? fm : nullptr, ctx);
         const double eu = MBPOL_ENGUNIT;
         const int o[2] = {list[3 * mi], list[3 * mj]};
+        if (valid) {
         sc[0] = E * eu;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
@@ -448,6 +468,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
                 for (int q = 0; q < 9; ++q) atomicAdd(p + n * q, 0.5 * eu * S[q]);
             }
         }
+        }   // valid
     }
     double v2[2] = {sc[0], sc[1]};
     block_reduce_add<2>(v2, O.scal + S_ENG2);
@@ -490,27 +511,37 @@ __global__ void k_flux(int natoms_real, OutPtrs O, const double* __restrict__ vx
 // ---------------------------------------------------------------------------------------------------------
 // batched per-cluster kernels (legacy ABI / KAT tests)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm)
+template <int ENGINE>
+__global__ void __launch_bounds__(256, 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const PolyCtx ctx{dyn_smem, tape};
+    const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ENGINE == 0 && t0_ >= n) return;
+    const int t = min(t0_, n - 1);
     double ww[18], gg[18], e, f[108];
     for (int i = 0; i < 18; ++i) ww[i] = w[(size_t)18 * t + i];
-    dimer_eval(ww, e, gg, fm ? f : nullptr);
+    dimer_eval<ENGINE>(ww, e, gg, fm ? f : nullptr, ctx);
+    if (t0_ >= n) return;
     E[t] = e;
     for (int i = 0; i < 18; ++i) g[(size_t)18 * t + i] = gg[i];
     if (fm)
         for (int i = 0; i < 108; ++i) fm[(size_t)108 * t + i] = f[i];
 }
 
-__global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm)
+template <int ENGINE>
+__global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const PolyCtx ctx{dyn_smem, tape};
+    const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ENGINE == 0 && t0_ >= n) return;
+    const int t = min(t0_, n - 1);
     double r[27], cv[36], gg[27], e;
 #pragma unroll
     for (int i = 0; i < 27; ++i) r[i] = w[(size_t)27 * t + i];
-    trimer_eval(r, e, cv);
+    trimer_eval<ENGINE>(r, e, cv, ctx);
+    if (t0_ >= n) return;
     trimer_gradient(r, cv, gg);
     E[t] = e;
 #pragma unroll
@@ -555,6 +586,27 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 // host side
 // =========================================================================================================
 std::once_flag g_const_once[16];
+double* g_tape2b[16] = {nullptr};
+double* g_tape3b[16] = {nullptr};
+
+// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape.  MBPOL_B200_ENGINE=ptx|tape overrides the default.
+#ifndef MBPOL_DEFAULT_ENGINE
+#define MBPOL_DEFAULT_ENGINE 0
+#endif
+int default_engine()
+{
+    const char* e = std::getenv("MBPOL_B200_ENGINE");
+    if (e && std::string(e) == "ptx") return 0;
+    if (e && std::string(e) == "tape") return 1;
+    return MBPOL_DEFAULT_ENGINE;
+}
+constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>);
+
+template <class K>
+cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 #define CUDA_TRY(h, call)                                                                                   \
     do {                                                                                                    \
@@ -588,7 +640,20 @@ int upload_constants(int device)
     const double d3[5] = {MBPOL_P3b_dHH_intra, MBPOL_P3b_dOH_intra, MBPOL_P3b_dHH, MBPOL_P3b_dOH, MBPOL_P3b_dOO};
     std::copy(k3, k3 + 5, P.k3); std::copy(d3, d3 + 5, P.d3);
     P.r3i = MBPOL_P3b_r3i; P.r3f = MBPOL_P3b_r3f;
-    (void)device;
+    if (cudaMemcpyToSymbol(c_tape_ops2b, TAPE2B_OPS_HOST, sizeof(TAPE2B_OPS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_ops3b, TAPE3B_OPS_HOST, sizeof(TAPE3B_OPS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_chunks2b, TAPE2B_CHUNKS_HOST, sizeof(TAPE2B_CHUNKS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_chunks3b, TAPE3B_CHUNKS_HOST, sizeof(TAPE3B_CHUNKS_HOST)) != cudaSuccess) return 1;
+    {   // coefficient tapes: one double per coefficient USE, in walk order (tools/gen_tape.py)
+        std::vector<double> t2(TAPE2B_NTAPE), t3(TAPE3B_NTAPE);
+        for (int i = 0; i < TAPE2B_NTAPE; ++i) t2[i] = TAPE2B_COEFIDX_HOST[i] < 0 ? 0.0 : MBPOL_COEF2B_HOST[TAPE2B_COEFIDX_HOST[i]];
+        for (int i = 0; i < TAPE3B_NTAPE; ++i) t3[i] = TAPE3B_COEFIDX_HOST[i] < 0 ? 0.0 : MBPOL_COEF3B_HOST[TAPE3B_COEFIDX_HOST[i]];
+        double *d2 = nullptr, *d3 = nullptr;
+        if (cudaMalloc(&d2, t2.size() * 8) != cudaSuccess || cudaMalloc(&d3, t3.size() * 8) != cudaSuccess) return 1;
+        if (cudaMemcpy(d2, t2.data(), t2.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        if (cudaMemcpy(d3, t3.data(), t3.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        g_tape2b[device] = d2; g_tape3b[device] = d3;
+    }
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(mbpol_coef2b, MBPOL_COEF2B_HOST, sizeof(double) * MBPOL_NCOEF2B) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(mbpol_coef3b, MBPOL_COEF3B_HOST, sizeof(double) * MBPOL_NCOEF3B) != cudaSuccess) return 1;
@@ -623,7 +688,7 @@ struct DevBuf {
 }  // namespace
 
 struct mbpol_b200_handle {
-    int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1;
+    int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1, engine = 1;
     int mxatms = 0, imcon = 0;
     bool have_vel = false, uploaded = false;
     std::string err;
@@ -693,7 +758,8 @@ int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle
     if (cudaSetDevice(device) != cudaSuccess) return MBPOL_B200_ECUDA;
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
-    h->device = device; h->nw = nttm2 / 3; h->flags = flags;
+    h->device = device; h->nw = nttm2 / 3; h->flags = flags; h->engine = default_engine();
+    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     *handle = h;
@@ -834,12 +900,16 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     OutPtrs O = h->views();
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     if (h->nd_shard > 0) {
-        k_dimers<<<(unsigned)((h->nd_shard + 255) / 256), 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        const unsigned gd = (unsigned)((h->nd_shard + 255) / 256);
+        if (h->engine) k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
+        else k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     if (h->nt_shard > 0) {
-        k_trimers<<<(unsigned)((h->nt_shard + 255) / 256), 256, 0, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        const unsigned gt = (unsigned)((h->nt_shard + 255) / 256);
+        if (h->engine) k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
+        else k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
@@ -981,8 +1051,15 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
     auto ok = [&](cudaError_t e) { if (e != cudaSuccess) rc = MBPOL_B200_ECUDA; return e == cudaSuccess; };
     if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
-        if (nat3 == 18) k_eval_dimers<<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm);
-        else k_eval_trimers<<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm);
+        const int eng = default_engine();
+        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); }
+        if (nat3 == 18) {
+            if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
+            else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
+        } else {
+            if (eng) k_eval_trimers<1><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
+            else k_eval_trimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
+        }
         ok(cudaGetLastError());
         ok(cudaDeviceSynchronize());
         ok(cudaMemcpy(E, dE, (size_t)n * 8, cudaMemcpyDeviceToHost));
