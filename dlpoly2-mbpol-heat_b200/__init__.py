@@ -22,7 +22,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmbpol_b200.so")
+LIB_PATH = os.environ.get("MBPOL_B200_LIB", os.path.join(HERE, "libmbpol_b200.so"))   # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "mbpol_b200.h")
 
 WANT_ATOMIC_ENERGY, WANT_FDECOMP, WANT_ATOMIC_STRESS = 1, 2, 4

@@ -28,10 +28,12 @@
 __constant__ double mbpol_coef2b[1153];
 __constant__ double mbpol_coef3b[1163];
 __constant__ MbpolParams mbpol_par;
-__constant__ unsigned c_tape_ops2b[TAPE2B_NOPS];
-__constant__ unsigned c_tape_ops3b[TAPE3B_NOPS];
-__constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][2];
-__constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][2];
+__constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
+__constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
+__constant__ unsigned c_tape_segs2b[TAPE2B_NSEGS];
+__constant__ unsigned c_tape_segs3b[TAPE3B_NSEGS];
+__constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][3];
+__constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
 
 namespace {
 
@@ -591,7 +593,7 @@ double* g_tape3b[16] = {nullptr};
 
 // polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape.  MBPOL_B200_ENGINE=ptx|tape overrides the default.
 #ifndef MBPOL_DEFAULT_ENGINE
-#define MBPOL_DEFAULT_ENGINE 0
+#define MBPOL_DEFAULT_ENGINE 1
 #endif
 int default_engine()
 {
@@ -640,8 +642,10 @@ int upload_constants(int device)
     const double d3[5] = {MBPOL_P3b_dHH_intra, MBPOL_P3b_dOH_intra, MBPOL_P3b_dHH, MBPOL_P3b_dOH, MBPOL_P3b_dOO};
     std::copy(k3, k3 + 5, P.k3); std::copy(d3, d3 + 5, P.d3);
     P.r3i = MBPOL_P3b_r3i; P.r3f = MBPOL_P3b_r3f;
-    if (cudaMemcpyToSymbol(c_tape_ops2b, TAPE2B_OPS_HOST, sizeof(TAPE2B_OPS_HOST)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(c_tape_ops3b, TAPE3B_OPS_HOST, sizeof(TAPE3B_OPS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_rowvars2b, TAPE2B_ROWVARS_HOST, sizeof(TAPE2B_ROWVARS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_rowvars3b, TAPE3B_ROWVARS_HOST, sizeof(TAPE3B_ROWVARS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_segs2b, TAPE2B_SEGS_HOST, sizeof(TAPE2B_SEGS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_segs3b, TAPE3B_SEGS_HOST, sizeof(TAPE3B_SEGS_HOST)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(c_tape_chunks2b, TAPE2B_CHUNKS_HOST, sizeof(TAPE2B_CHUNKS_HOST)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(c_tape_chunks3b, TAPE3B_CHUNKS_HOST, sizeof(TAPE3B_CHUNKS_HOST)) != cudaSuccess) return 1;
     {   // coefficient tapes: one double per coefficient USE, in walk order (tools/gen_tape.py)

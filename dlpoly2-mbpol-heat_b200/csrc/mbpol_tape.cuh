@@ -19,13 +19,55 @@ __device__ __forceinline__ double tape_lds(unsigned a)
 __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 #define TAPE_LDS_V2(vx, vy, addr, imm) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "r"(addr), "n"(imm))
 
+// ---- per-row prologue / epilogue shared by every row type (used by the generated TAPE*_SEGMENT_SWITCH) ----
+#define TAPE_COL (TAPE_BS * 8)       /* bytes between two variables' columns */
+#ifndef TAPE_UNROLL
+#define TAPE_UNROLL 2
+#endif
+#define TAPE_PRAGMA_(x) _Pragma(#x)
+#define TAPE_PRAGMA(x) TAPE_PRAGMA_(x)
+#define TAPE_ROW_LOOP(nrows) TAPE_PRAGMA(unroll TAPE_UNROLL) for (unsigned r_ = 0; r_ < (nrows); ++r_)
+// The row header -- (u,w,v) word, the three x loads and the first tape pair -- is software pipelined: the header of
+// the NEXT row (nu_/nw_/nv_, nxu/nxw/nxv, nq0x/nq0y; loaded by TAPE_ROW_FETCH) is issued before the FMAs of this row.
+#define TAPE_ROW_FETCH(ROWIDX, CP)                                                                       \
+    {                                                                                                    \
+        const unsigned vw_ = rowvars[ROWIDX];                                                            \
+        nu_ = xs_t + (vw_ & 255u) * TAPE_COL;                                                            \
+        nw_ = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL;                                                     \
+        nv_ = xs_t + (vw_ >> 16) * TAPE_COL;                                                             \
+        nxu = tape_lds(nu_); nxw = tape_lds(nw_); nxv = tape_lds(nv_);                                   \
+        TAPE_LDS_V2(nq0x, nq0y, CP, 0);                                                                  \
+    }
+#define TAPE_ROW_PRE(ROWBYTES)                                                                           \
+    const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
+    const double xu = nxu, xw = nxw, xv = nxv, q0x = nq0x, q0y = nq0y;                                   \
+    const double p2 = xv * xw, P = p2 * xu;                                                              \
+    double S0 = q0x, S1 = 0.0;                                                                           \
+    TAPE_ROW_FETCH(min(row + 1, row_last), cp + (ROWBYTES))
+#ifdef TAPE_EXPERIMENT_SKIP_WV   /* timing experiment only: WRONG gradients */
+#define TAPE_WV_UPDATES e = fma(S0, xu * xv + xu * xw, e);
+#else
+#define TAPE_WV_UPDATES                                                                                  \
+    tape_sts(aw_ + gs_delta, fma(S0, xu * xv, tape_lds(aw_ + gs_delta)));                                \
+    tape_sts(av_ + gs_delta, fma(S0, xu * xw, tape_lds(av_ + gs_delta)));
+#endif
+#define TAPE_ROW_POST(ROWBYTES)                                                                          \
+    S0 += S1;                                                                                            \
+    e = fma(S0, P, e);                                                                                   \
+    tape_sts(au_ + gs_delta, fma(S0, p2, tape_lds(au_ + gs_delta)));                                     \
+    TAPE_WV_UPDATES                                                                                      \
+    cp += (ROWBYTES);                                                                                    \
+    ++row;
+
 #include "gen/tape_2b.h"
 #include "gen/tape_3b.h"
 
-extern __constant__ unsigned c_tape_ops2b[TAPE2B_NOPS];
-extern __constant__ unsigned c_tape_ops3b[TAPE3B_NOPS];
-extern __constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][2];
-extern __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][2];
+extern __constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
+extern __constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
+extern __constant__ unsigned c_tape_segs2b[TAPE2B_NSEGS];
+extern __constant__ unsigned c_tape_segs3b[TAPE3B_NSEGS];
+extern __constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][3];
+extern __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
 
 template <int NV>
 struct TapeSmem {   // dynamic shared memory layout
@@ -46,30 +88,30 @@ __device__ __forceinline__ void tape_cp_wait() { asm volatile("cp.async.wait_gro
 template <int WHICH, int NV>
 __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, double (&x)[NV], double (&g)[NV], double& E, TapeSmem<NV>& sm)
 {
-    constexpr int NTYPES = (WHICH == 3) ? TAPE3B_NTYPES : TAPE2B_NTYPES;
     constexpr int nchunks = (WHICH == 3) ? TAPE3B_NCHUNKS : TAPE2B_NCHUNKS;
-    const unsigned* ops = (WHICH == 3) ? c_tape_ops3b : c_tape_ops2b;
-    const int(*chunks)[2] = (WHICH == 3) ? c_tape_chunks3b : c_tape_chunks2b;
+    const unsigned* rowvars = (WHICH == 3) ? c_tape_rowvars3b : c_tape_rowvars2b;
+    const unsigned* segs = (WHICH == 3) ? c_tape_segs3b : c_tape_segs2b;
+    const int(*chunks)[3] = (WHICH == 3) ? c_tape_chunks3b : c_tape_chunks2b;
     const unsigned tid = threadIdx.x;
     const unsigned buf0 = (unsigned)__cvta_generic_to_shared(&sm.buf[0][0]);
-    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);   // + var * (TAPE_BS*8)
-    const unsigned gs_t = (unsigned)__cvta_generic_to_shared(&sm.gs[0][tid]);
+    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
+    const unsigned gs_delta = (unsigned)sizeof(sm.xs);                       // gs column = xs column + gs_delta
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
-        tape_sts(xs_t + c * (TAPE_BS * 8), x[c]);
-        tape_sts(gs_t + c * (TAPE_BS * 8), 0.0);
+        tape_sts(xs_t + c * TAPE_COL, x[c]);
+        tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
         g[c] = 0.0;
     }
-    tape_sts(xs_t + NV * (TAPE_BS * 8), 1.0);
-    tape_sts(gs_t + NV * (TAPE_BS * 8), 0.0);
+    tape_sts(xs_t + NV * TAPE_COL, 1.0);
+    tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
     auto stage = [&](int k) {
-        const int t0 = chunks[k][1], n = chunks[k + 1][1] - t0;      // both even: 16-byte granules
+        const int t0 = chunks[k][2], n = chunks[k + 1][2] - t0;      // both even: 16-byte granules
         const unsigned dst = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
         for (int i = 2 * tid; i < n; i += 2 * TAPE_BS) tape_cp_async16(dst + 8 * i, tape + t0 + i);
         tape_cp_commit();
     };
     stage(0);
-    double e = 0.0, s1 = 0.0, s2 = 0.0, xv = 0.0, xw = 0.0, p2 = 0.0;
+    double e = 0.0;
     for (int k = 0; k < nchunks; ++k) {
         if (k + 1 < nchunks) {
             stage(k + 1);
@@ -79,47 +121,24 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
         }
         __syncthreads();                                   // chunk k visible to every thread
         unsigned cp = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
-        const int o1 = chunks[k + 1][0];
-        for (int oi = chunks[k][0]; oi < o1; ++oi) {
-            const unsigned op = ops[oi];
-            const unsigned h = op & 255u, voff = (op >> 20) * (TAPE_BS * 8);
-            if (h < NTYPES) {                              // NODE3: one row of leaves under the product P = p2 * x[u]
-                const double xu = tape_lds(xs_t + voff);
-                double q0x, q0y;
-                TAPE_LDS_V2(q0x, q0y, cp, 0);
-                const double P = p2 * xu;
-                double S0 = q0x, S1 = 0.0;
-                if (WHICH == 3) {
-                    TAPE3B_ROW_SWITCH(h, cp, S0, S1, P, q0x, q0y)
-                } else {
-                    TAPE2B_ROW_SWITCH(h, cp, S0, S1, P, q0x, q0y)
-                }
-                S0 += S1;
-                s2 = fma(S0, xu, s2);
-                tape_sts(gs_t + voff, fma(S0, p2, tape_lds(gs_t + voff)));
-            } else if (h == NTYPES + 1) {                  // ENTER2
-                xw = tape_lds(xs_t + voff);
-                p2 = xv * xw;
-                s2 = tape_lds(cp);
-            } else if (h == NTYPES + 2) {                  // EXIT2
-                s1 = fma(s2, xw, s1);
-                tape_sts(gs_t + voff, fma(s2, xv, tape_lds(gs_t + voff)));
-            } else if (h == NTYPES + 0) {                  // ENTER1
-                xv = tape_lds(xs_t + voff);
-                s1 = tape_lds(cp);
-            } else if (h == NTYPES + 3) {                  // EXIT1
-                e = fma(s1, xv, e);
-                tape_sts(gs_t + voff, tape_lds(gs_t + voff) + s1);
-            } else {                                       // LIN
-                const double a = tape_lds(cp);
-                e = fma(a, tape_lds(xs_t + voff), e);
-                tape_sts(gs_t + voff, tape_lds(gs_t + voff) + a);
+        unsigned row = chunks[k][1];
+        const unsigned row_last = chunks[k + 1][1] - 1;    // last row of this chunk (prefetch clamp)
+        const int sg1 = chunks[k + 1][0];
+        unsigned nu_, nw_, nv_;
+        double nxu, nxw, nxv, nq0x, nq0y;
+        TAPE_ROW_FETCH(row, cp)
+        for (int sg = chunks[k][0]; sg < sg1; ++sg) {
+            const unsigned seg = segs[sg];
+            const unsigned type = seg & 255u, nrows = seg >> 8;
+            if (WHICH == 3) {
+                TAPE3B_SEGMENT_SWITCH(type, nrows)
+            } else {
+                TAPE2B_SEGMENT_SWITCH(type, nrows)
             }
-            cp += (op >> 8) & 0xfffu;
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }
 #pragma unroll
-    for (int c = 0; c < NV; ++c) g[c] += tape_lds(gs_t + c * (TAPE_BS * 8));
+    for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);
     E = e;
 }
