@@ -42,7 +42,7 @@ __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("s
     const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
     const double xu = nxu, xw = nxw, xv = nxv, q0x = nq0x, q0y = nq0y;                                   \
     const double p2 = xv * xw, P = p2 * xu;                                                              \
-    double S0 = q0x, S1 = 0.0;                                                                           \
+    double S0 = q0x, S1 = 0.0, S2 = 0.0, S3 = 0.0;                                                       \
     TAPE_ROW_FETCH(min(row + 1, row_last), cp + (ROWBYTES))
 #ifdef TAPE_EXPERIMENT_SKIP_WV   /* timing experiment only: WRONG gradients */
 #define TAPE_WV_UPDATES e = fma(S0, xu * xv + xu * xw, e);
@@ -52,7 +52,7 @@ __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("s
     tape_sts(av_ + gs_delta, fma(S0, xu * xw, tape_lds(av_ + gs_delta)));
 #endif
 #define TAPE_ROW_POST(ROWBYTES)                                                                          \
-    S0 += S1;                                                                                            \
+    S0 = (S0 + S1) + (S2 + S3);                                                                          \
     e = fma(S0, P, e);                                                                                   \
     tape_sts(au_ + gs_delta, fma(S0, p2, tape_lds(au_ + gs_delta)));                                     \
     TAPE_WV_UPDATES                                                                                      \

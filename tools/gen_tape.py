@@ -35,6 +35,7 @@ import gen_poly as G
 
 OUTD = G.OUTD
 CHUNK = 1024          # doubles per staged tape chunk (8 KB)
+NSUM = 2              # independent partial sums of the Horner accumulator S (shortens the dependent DFMA chain)
 
 
 def build(tag, mono, nv, mode):
@@ -112,7 +113,7 @@ def emit_header(tag, nv, rows, types, mode):
     L = ["// generated by tools/gen_tape.py (%s, trie order=%s) -- do not edit" % (tag, mode), "#pragma once",
          "#define TAPE%s_NV %d" % (T, nv), "#define TAPE%s_NROWS %d" % (T, len(rows)), "#define TAPE%s_NTAPE %d" % (T, len(tape)),
          "#define TAPE%s_NSEGS %d" % (T, len(segs)), "#define TAPE%s_NCHUNKS %d" % (T, len(chunks) - 1),
-         "#define TAPE%s_NTYPES %d" % (T, nt), "#define TAPE%s_FP64_INSTR %d" % (T, nfma), "#define TAPE_CHUNK_DOUBLES %d" % CHUNK]
+         "#define TAPE%s_NTYPES %d" % (T, nt), "#define TAPE%s_FP64_INSTR %d" % (T, nfma), "#define TAPE_CHUNK_DOUBLES %d" % CHUNK, "#define TAPE_NSUM %d" % NSUM]
     L.append("static const unsigned TAPE%s_ROWVARS_HOST[%d] = {%s};" % (T, len(rowvars), ",".join(str(w) for w in rowvars)))
     L.append("static const unsigned TAPE%s_SEGS_HOST[%d] = {%s};" % (T, len(segs), ",".join(str(w) for w in segs)))
     L.append("static const short TAPE%s_COEFIDX_HOST[%d] = {%s};" % (T, len(tape), ",".join(str(c) for c in tape)))
@@ -131,7 +132,7 @@ def emit_header(tag, nv, rows, types, mode):
                 have.add(pair)
                 body.append("double q%dx, q%dy; TAPE_LDS_V2(q%dx, q%dy, cp, %d);" % (pair, pair, pair, pair, 16 * pair))
             a = "q%d%s" % (pair, "xy"[lane])
-            acc = "S0" if i % 2 == 0 else "S1"
+            acc = "S%d" % (i % NSUM)
             body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, P, g[%d]);" % (acc, a, v, acc, v, a, v))
         L.append("case %d: TAPE_ROW_LOOP(nrows) { TAPE_ROW_PRE(%d) %s TAPE_ROW_POST(%d) } break; \\" % (
             t, 8 * row_slots(len(vs)), " ".join(body), 8 * row_slots(len(vs))))
@@ -144,7 +145,9 @@ def main():
     ap.add_argument("--outdir", default=OUTD)
     ap.add_argument("--order2b", default="identity")
     ap.add_argument("--order3b", default="reverse")
+    ap.add_argument("--nsum", type=int, default=NSUM)
     args = ap.parse_args()
+    globals()["NSUM"] = args.nsum
     d = np.load(G.DATA)
     os.makedirs(args.outdir, exist_ok=True)
     for tag, nv, mode in (("2b", 31, args.order2b), ("3b", 36, args.order3b)):
