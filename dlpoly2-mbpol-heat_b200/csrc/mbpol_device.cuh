@@ -9,8 +9,7 @@
 #include "mbpol_tape.cuh"
 
 // linear coefficients: referenced by name from the generated PTX (.extern .const)
-extern __constant__ double mbpol_coef2b[1153];
-extern __constant__ double mbpol_coef3b[1163];
+extern __constant__ double mbpol_cwin[];   // the single constant-bank window: PTX-engine coefficient tables or one tape window
 
 struct MbpolParams {   // non-linear parameters, mbpol-2b-poly.cpp:1846-1866, mbpol-3b-poly.cpp:1486-1503
     double k2[8];       // HH_intra, OH_intra, HH_coul, OH_coul, OO_coul, XH, XO, XX
@@ -97,12 +96,9 @@ __device__ constexpr int V3K[36] = {0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2,
 // r[27]: imaged coordinates (any common origin).  Outputs in kcal/mol:
 //   E, cv[n] with  dE/dr_a += cv[n]*(r_a - r_b),  dE/dr_b -= ...   for variable n = (a,b); the three switch-gradient
 //   terms (mbpol-3b-poly.cpp:292-309) are folded into cv[33..35] because they act along the same O-O vectors.
-template <int ENGINE>
-__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+// variables x_n = exp(-k (d - d0)) and 1/d of the 36 pair distances
+__device__ __forceinline__ void trimer_variables(const double (&r)[27], double* xv, double (&rinv)[36])
 {
-    double xv[ENGINE ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE ? 36 : 1];
-    double* gp = ENGINE ? gp_ : xv + 37;      // ENGINE 0: x and g live in the per-thread record (local memory)
-    double rinv[36];
 #pragma unroll
     for (int n = 0; n < 36; ++n) {
         const int a = 3 * V3A[n], b = 3 * V3B[n];
@@ -111,14 +107,12 @@ __device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, do
         rinv[n] = 1.0 / d;
         xv[n] = exp(-mbpol_par.k3[V3K[n]] * (d - mbpol_par.d3[V3K[n]]));
     }
-    double Epoly;
-    if (ENGINE == 0) {
-        POLY3B_CALL_ALL(xv, 1u);
-        Epoly = xv[36];
-    } else {
-        tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
-                         *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
-    }
+}
+
+// switch + chain rule: (x, dEpoly/dx, Epoly) -> E and the per-variable force coefficients cv
+__device__ __forceinline__ void trimer_finish(const double* xv, const double* gp, double Epoly, const double (&rinv)[36], double& E,
+                                              double (&cv)[36])
+{
     // switch on the three O-O distances: rinv[33..35] = 1/|Oa-Ob|, 1/|Oa-Oc|, 1/|Ob-Oc|
     const double drab = 1.0 / rinv[33], drac = 1.0 / rinv[34], drbc = 1.0 / rinv[35];
     double gab, gac, gbc;
@@ -133,6 +127,24 @@ __device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, do
     cv[34] += gac * (sab + sbc) * Epoly * rinv[34];
     cv[35] += gbc * (sab + sac) * Epoly * rinv[35];
     E = s * Epoly;
+}
+
+template <int ENGINE>
+__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+{
+    double xv[ENGINE ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE ? 36 : 1];
+    double* gp = ENGINE ? gp_ : xv + 37;      // ENGINE 0: x and g live in the per-thread record (local memory)
+    double rinv[36];
+    trimer_variables(r, xv, rinv);
+    double Epoly;
+    if (ENGINE == 0) {
+        POLY3B_CALL_ALL(xv, 1u);
+        Epoly = xv[36];
+    } else {
+        tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
+                         *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    }
+    trimer_finish(xv, gp, Epoly, rinv, E, cv);
 }
 
 // gradient on the 9 atoms from cv:  g[3*atom + c]

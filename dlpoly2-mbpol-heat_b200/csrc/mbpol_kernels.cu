@@ -25,8 +25,11 @@
 #include "gen/mbpol_model_data.h"
 #include <cstdlib>
 
-__constant__ double mbpol_coef2b[1153];
-__constant__ double mbpol_coef3b[1163];
+__constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];   // PTX-engine coefficient tables [2B | 3B] or one constant-tape window
+__constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
+__constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
+__constant__ int c_tape_cpass2b[TAPE2B_NCPASS + 1][3];
+__constant__ int c_tape_cpass3b[TAPE3B_NCPASS + 1][3];
 __constant__ MbpolParams mbpol_par;
 __constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
 __constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
@@ -268,6 +271,111 @@ __device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, cons
 // ---------------------------------------------------------------------------------------------------------
 // K3: trimers.  One thread per accepted trimer of this shard.
 // ---------------------------------------------------------------------------------------------------------
+// imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
+__device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict__ mono, const CellInfo& C, int mi, int mj, int mk, double (&r)[27])
+{
+    double wj[9], wi[9], wk[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        wi[c] = mono[(size_t)c * nw + mi];
+        wj[c] = mono[(size_t)c * nw + mj];
+        wk[c] = mono[(size_t)c * nw + mk];
+    }
+    double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+    double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
+    image_vec(C, a0, a1, a2);
+    image_vec(C, b0, b1, b2);
+    const double ra[3] = {a0, a1, a2}, rb[3] = {b0, b1, b2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[c] = ra[c];                               // O_i' - O_j
+        r[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+        r[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+        r[9 + c] = 0.0;
+        r[12 + c] = wj[3 + c] - wj[c];
+        r[15 + c] = wj[6 + c] - wj[c];
+        r[18 + c] = -rb[c];                         // O_k' - O_j
+        r[21 + c] = (wk[3 + c] - wk[c]) - rb[c];
+        r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
+    }
+}
+
+// accumulation of one evaluated trimer (mbpol.f90:896-1267): forces, per-atom energy, W, S; returns the block scalars
+__device__ __forceinline__ void trimer_scatter(const double (&r)[27], double E, const double (&cv)[36], const int (&o)[3],
+                                               const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
+                                               const OutPtrs& O, int flags, double (&sc)[8])
+{
+    double g[27];
+    trimer_gradient(r, cv, g);
+    const double eu = MBPOL_ENGUNIT;
+    sc[0] = E * eu;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        const int atom = o[a / 3] - 1 + (a % 3);
+        const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
+        atomicAdd(O.fx + atom, -gx);
+        atomicAdd(O.fy + atom, -gy);
+        atomicAdd(O.fz + atom, -gz);
+        sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
+        sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
+        sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
+    }
+    if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
+        const double e9 = (1.0 / 9.0) * E * eu;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e9);
+    }
+    if (flags & MBPOL_B200_WANT_FDECOMP) {
+        double xs[3] = {0, 0, 0}, xraw[27];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const int atom = o[a / 3] - 1 + (a % 3);
+            xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
+            xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
+        }
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            const double f[3] = {-(1.0 / 9.0) * g[3 * a] * eu, -(1.0 / 9.0) * g[3 * a + 1] * eu, -(1.0 / 9.0) * g[3 * a + 2] * eu};
+            scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 9, f);
+        }
+    }
+    if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {
+        // S_i(a,b) = 1/2*eu*sum_{j != i} (r_i-r_j)_a FM[i][j]_b with FM[i][j] = cv_n (r_i - r_j): a symmetric
+        // tensor cv_n d (x) d that goes to BOTH atoms of variable n (mbpol.f90:945-966)
+        double S[9][6];
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) S[a][q] = 0.0;
+#pragma unroll
+        for (int n = 0; n < 36; ++n) {
+            const int a = V3A[n], b = V3B[n];
+            const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
+            const double h = 0.5 * eu * cv[n];
+            const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
+        }
+        const size_t n = O.mxatms;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+            double* p = O.astress + o[a / 3] - 1 + (a % 3);
+            atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
+            atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
+            atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
+        }
+    }
+}
+
+__device__ __forceinline__ void trimer_block_scalars(double (&sc)[8], const OutPtrs& O)
+{
+    double v2[2] = {sc[0], sc[1]};
+    block_reduce_add<2>(v2, O.scal + S_ENG3);
+    __syncthreads();
+    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
+    block_reduce_add<9>(st, O.scal + S_STRESS);
+}
+
 template <int ENGINE>
 __global__ void __launch_bounds__(256, 1)
 k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
@@ -283,103 +391,60 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
     if (ENGINE == 1 || valid) {
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
         double r[27];
-        // imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
-        double wj[9], wi[9], wk[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            wi[c] = mono[(size_t)c * nw + mi];
-            wj[c] = mono[(size_t)c * nw + mj];
-            wk[c] = mono[(size_t)c * nw + mk];
-        }
-        double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
-        double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
-        image_vec(C, a0, a1, a2);
-        image_vec(C, b0, b1, b2);
-        const double ra[3] = {a0, a1, a2}, rb[3] = {b0, b1, b2};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            r[c] = ra[c];                               // O_i' - O_j
-            r[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
-            r[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
-            r[9 + c] = 0.0;
-            r[12 + c] = wj[3 + c] - wj[c];
-            r[15 + c] = wj[6 + c] - wj[c];
-            r[18 + c] = -rb[c];                         // O_k' - O_j
-            r[21 + c] = (wk[3 + c] - wk[c]) - rb[c];
-            r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
-        }
+        trimer_geometry(nw, mono, C, mi, mj, mk, r);
         double E, cv[36];
         trimer_eval<ENGINE>(r, E, cv, ctx);
-        double g[27];
-        trimer_gradient(r, cv, g);
-        const double eu = MBPOL_ENGUNIT;
         const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
-        if (valid) {
-        sc[0] = E * eu;
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const int atom = o[a / 3] - 1 + (a % 3);
-            const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
-            atomicAdd(O.fx + atom, -gx);
-            atomicAdd(O.fy + atom, -gy);
-            atomicAdd(O.fz + atom, -gz);
-            sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
-            sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
-            sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
-        }
-        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
-            const double e9 = (1.0 / 9.0) * E * eu;
-#pragma unroll
-            for (int a = 0; a < 9; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e9);
-        }
-        if (flags & MBPOL_B200_WANT_FDECOMP) {
-            double xs[3] = {0, 0, 0}, xraw[27];
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                const int atom = o[a / 3] - 1 + (a % 3);
-                xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
-                xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
-            }
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                const double f[3] = {-(1.0 / 9.0) * g[3 * a] * eu, -(1.0 / 9.0) * g[3 * a + 1] * eu, -(1.0 / 9.0) * g[3 * a + 2] * eu};
-                scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 9, f);
-            }
-        }
-        if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {
-            // S_i(a,b) = 1/2*eu*sum_{j != i} (r_i-r_j)_a FM[i][j]_b with FM[i][j] = cv_n (r_i - r_j): a symmetric
-            // tensor cv_n d (x) d that goes to BOTH atoms of variable n (mbpol.f90:945-966)
-            double S[9][6];
-#pragma unroll
-            for (int a = 0; a < 9; ++a)
-#pragma unroll
-                for (int q = 0; q < 6; ++q) S[a][q] = 0.0;
-#pragma unroll
-            for (int n = 0; n < 36; ++n) {
-                const int a = V3A[n], b = V3B[n];
-                const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
-                const double h = 0.5 * eu * cv[n];
-                const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
-#pragma unroll
-                for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
-            }
-            const size_t n = O.mxatms;
-#pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                double* p = O.astress + o[a / 3] - 1 + (a % 3);
-                atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
-                atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
-                atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
-            }
-        }
-        }   // valid
+        if (valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
     }
-    // scalars: eng3, vir3, stress (symmetric fill: 2,3,4 / 3?,...)  -> scal[S_ENG3], scal[S_VIR3], scal[S_STRESS+..]
-    double v2[2] = {sc[0], sc[1]};
-    block_reduce_add<2>(v2, O.scal + S_ENG3);
-    __syncthreads();
-    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
-    block_reduce_add<9>(st, O.scal + S_STRESS);
+    trimer_block_scalars(sc, O);
+}
+
+// Engine 2 (constant-bank tape): one launch per constant window.  gbuf[c * ntri + t], c = 0..36: partial (g[36], E)
+// of trimer t between the passes (coalesced SoA in HBM).  The last pass runs the chain rule and the scatter.
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(256, 1)
+k_trimers_cpass(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
+                const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
+                int pass, double* __restrict__ gbuf)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    // no thread-dependent control flow around the row loops: the tape index must stay provably warp-uniform so that the
+    // coefficient loads compile to LDCU (uniform datapath).  Idle lanes shadow the last trimer and skip the stores.
+    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t0_ < ntri;
+    const long long t = valid ? t0_ : ntri - 1;
+    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
+        double r[27];
+        trimer_geometry(nw, mono, C, mi, mj, mk, r);
+        double xv[36], rinv[36], gp[36], Epoly;
+        trimer_variables(r, xv, rinv);
+        if (FIRST) {
+#pragma unroll
+            for (int c = 0; c < 36; ++c) gp[c] = 0.0;
+            Epoly = 0.0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 36; ++c) gp[c] = gbuf[(size_t)c * ntri + t];
+            Epoly = gbuf[(size_t)36 * ntri + t];
+        }
+        tape_eval_const_pass<3, 36>(pass, xv, gp, Epoly, *reinterpret_cast<TapeCSmem<36>*>(dyn_smem));
+        if (!LAST) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 36; ++c) gbuf[(size_t)c * ntri + t] = gp[c];
+                gbuf[(size_t)36 * ntri + t] = Epoly;
+            }
+        } else {
+            double E, cv[36];
+            trimer_finish(xv, gp, Epoly, rinv, E, cv);
+            const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};
+            if (valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
+        }
+    }
+    if (LAST) trimer_block_scalars(sc, O);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -590,8 +655,17 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 std::once_flag g_const_once[16];
 double* g_tape2b[16] = {nullptr};
 double* g_tape3b[16] = {nullptr};
+double* g_coefwin[16] = {nullptr};
 
-// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape.  MBPOL_B200_ENGINE=ptx|tape overrides the default.
+// (re)fill the constant-bank window, ordered on `s` behind the kernels that read the previous content
+cudaError_t load_window(const double* dsrc, size_t ndoubles, cudaStream_t s)
+{
+    return cudaMemcpyToSymbolAsync(mbpol_cwin, dsrc, ndoubles * 8, 0, cudaMemcpyDeviceToDevice, s);
+}
+cudaError_t load_coef_window(int device, cudaStream_t s) { return load_window(g_coefwin[device], MBPOL_NCOEF2B + MBPOL_NCOEF3B, s); }
+
+// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory, 2 = coefficient tape in
+// the constant bank (3B in NCPASS launches; 2B uses engine 1).  MBPOL_B200_ENGINE=ptx|tape|ctape overrides the default.
 #ifndef MBPOL_DEFAULT_ENGINE
 #define MBPOL_DEFAULT_ENGINE 1
 #endif
@@ -600,9 +674,10 @@ int default_engine()
     const char* e = std::getenv("MBPOL_B200_ENGINE");
     if (e && std::string(e) == "ptx") return 0;
     if (e && std::string(e) == "tape") return 1;
+    if (e && std::string(e) == "ctape") return 2;
     return MBPOL_DEFAULT_ENGINE;
 }
-constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>);
+constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM3C = sizeof(TapeCSmem<36>);
 
 template <class K>
 cudaError_t allow_smem(K kernel, size_t bytes)
@@ -659,8 +734,19 @@ int upload_constants(int device)
         g_tape2b[device] = d2; g_tape3b[device] = d3;
     }
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(mbpol_coef2b, MBPOL_COEF2B_HOST, sizeof(double) * MBPOL_NCOEF2B) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(mbpol_coef3b, MBPOL_COEF3B_HOST, sizeof(double) * MBPOL_NCOEF3B) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_csegs2b, TAPE2B_CSEGS_HOST, sizeof(TAPE2B_CSEGS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_csegs3b, TAPE3B_CSEGS_HOST, sizeof(TAPE3B_CSEGS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_cpass2b, TAPE2B_CPASS_HOST, sizeof(TAPE2B_CPASS_HOST)) != cudaSuccess) return 1;
+    if (cudaMemcpyToSymbol(c_tape_cpass3b, TAPE3B_CPASS_HOST, sizeof(TAPE3B_CPASS_HOST)) != cudaSuccess) return 1;
+    {   // PTX engine: both coefficient tables as one device image of the constant window
+        std::vector<double> w(MBPOL_NCOEF2B + MBPOL_NCOEF3B);
+        std::copy(MBPOL_COEF2B_HOST, MBPOL_COEF2B_HOST + MBPOL_NCOEF2B, w.begin());
+        std::copy(MBPOL_COEF3B_HOST, MBPOL_COEF3B_HOST + MBPOL_NCOEF3B, w.begin() + MBPOL_NCOEF2B);
+        double* d = nullptr;
+        if (cudaMalloc(&d, w.size() * 8) != cudaSuccess) return 1;
+        if (cudaMemcpy(d, w.data(), w.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        g_coefwin[device] = d;
+    }
     return 0;
 }
 
@@ -701,7 +787,7 @@ struct mbpol_b200_handle {
     CellInfo C;
     Grid G;
     int ncells = 0;
-    DevBuf<double> xyz, vel, mono, out;
+    DevBuf<double> xyz, vel, mono, out, gbuf;
     DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag;
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll;
@@ -763,7 +849,12 @@ int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
     h->device = device; h->nw = nttm2 / 3; h->flags = flags; h->engine = default_engine();
-    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
+        allow_smem(k_trimers_cpass<true, false>, SMEM3C) != cudaSuccess || allow_smem(k_trimers_cpass<false, false>, SMEM3C) != cudaSuccess ||
+        allow_smem(k_trimers_cpass<false, true>, SMEM3C) != cudaSuccess || allow_smem(k_trimers_cpass<true, true>, SMEM3C) != cudaSuccess) {
+        delete h;
+        return MBPOL_B200_ECUDA;
+    }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     *handle = h;
@@ -906,14 +997,37 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     if (h->nd_shard > 0) {
         const unsigned gd = (unsigned)((h->nd_shard + 255) / 256);
         if (h->engine) k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
-        else k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+        else {
+            CUDA_TRY(h, load_coef_window(h->device, s));
+            k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+        }
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     if (h->nt_shard > 0) {
         const unsigned gt = (unsigned)((h->nt_shard + 255) / 256);
-        if (h->engine) k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
-        else k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, h->trimers.p + 3 * t0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+        const int* tl = h->trimers.p + 3 * t0;
+        if (h->engine == 2) {
+            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * h->nt_shard));
+            for (int p = 0; p < TAPE3B_NCPASS; ++p) {
+                const int tb = TAPE3B_CPASS_HOST[p][2], te = TAPE3B_CPASS_HOST[p + 1][2];
+                CUDA_TRY(h, load_window(g_tape3b[h->device] + tb, te - tb, s));
+                const bool first = p == 0, last = p == TAPE3B_NCPASS - 1;
+#define CPASS_LAUNCH(F, L) k_trimers_cpass<F, L><<<gt, 256, SMEM3C, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, p, h->gbuf.p)
+                if (first && last) CPASS_LAUNCH(true, true);
+                else if (first) CPASS_LAUNCH(true, false);
+                else if (last) CPASS_LAUNCH(false, true);
+                else CPASS_LAUNCH(false, false);
+#undef CPASS_LAUNCH
+                ++h->launches;
+            }
+            --h->launches;
+        } else if (h->engine == 1) {
+            k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
+        } else {
+            CUDA_TRY(h, load_coef_window(h->device, s));
+            k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+        }
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
@@ -1057,6 +1171,7 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
         const int eng = default_engine();
         if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); }
+        else ok(load_coef_window(device, 0));
         if (nat3 == 18) {
             if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
             else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);

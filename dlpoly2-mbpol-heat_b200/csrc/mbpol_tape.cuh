@@ -18,6 +18,7 @@ __device__ __forceinline__ double tape_lds(unsigned a)
 }
 __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 #define TAPE_LDS_V2(vx, vy, addr, imm) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "r"(addr), "n"(imm))
+#define TAPE_LD2(vx, vy, addr, imm) TAPE_LDS_V2(vx, vy, addr, imm)      /* engine 1: tape pairs come from shared memory */
 
 // ---- per-row prologue / epilogue shared by every row type (used by the generated TAPE*_SEGMENT_SWITCH) ----
 #define TAPE_COL (TAPE_BS * 8)       /* bytes between two variables' columns */
@@ -137,6 +138,98 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
             }
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);
+    E = e;
+}
+
+
+// =========================================================================================================
+// Engine 2: the same rows, but the coefficient tape is read from the CONSTANT BANK (warp-uniform operands, no
+// 32-lane write-back through the LSU -- experiments/README.md section 2, last row).  The bank holds one window of
+// <= TAPE_CWINDOW_DOUBLES slots, so a polynomial takes NCPASS kernel launches; the host copies the next window into
+// mbpol_cwin between launches (stream ordered) and the partial (E, g) of every cluster travels through HBM.
+// No barriers: threads are independent here.
+// =========================================================================================================
+extern __constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];
+extern __constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
+extern __constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
+extern __constant__ int c_tape_cpass2b[TAPE2B_NCPASS + 1][3];
+extern __constant__ int c_tape_cpass3b[TAPE3B_NCPASS + 1][3];
+
+template <int NV>
+struct TapeCSmem {
+    double xs[NV + 1][TAPE_BS];
+    double gs[NV + 1][TAPE_BS];
+};
+
+#undef TAPE_LD2
+#undef TAPE_ROW_FETCH
+#undef TAPE_ROW_PRE
+#undef TAPE_ROW_POST
+/* the tape pointer is a .const-space address kept opaque to the optimiser (inline PTX), so that ptxas sees a clean
+   warp-uniform chain  mov -> add imm -> ld.const [reg+imm]  and emits LDCU with a uniform-register base */
+#define TAPE_LD2(vx, vy, ca, imm) asm volatile("ld.const.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "l"(ca), "n"(imm))
+#define TAPE_ADVANCE(ca, bytes) asm volatile("add.u64 %0, %0, %1;" : "+l"(ca) : "n"(bytes))
+#define TAPE_ROW_FETCH(ROWIDX)                                                                           \
+    {                                                                                                    \
+        const unsigned vw_ = rowvars[ROWIDX];                                                            \
+        nu_ = xs_t + (vw_ & 255u) * TAPE_COL;                                                            \
+        nw_ = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL;                                                     \
+        nv_ = xs_t + (vw_ >> 16) * TAPE_COL;                                                             \
+        nxu = tape_lds(nu_); nxw = tape_lds(nw_); nxv = tape_lds(nv_);                                   \
+    }
+#define TAPE_ROW_PRE(ROWBYTES)                                                                           \
+    const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
+    const double xu = nxu, xw = nxw, xv = nxv;                                                           \
+    double q0x, q0y;                                                                                     \
+    TAPE_LD2(q0x, q0y, cp, 0);                                                                           \
+    const double p2 = xv * xw, P = p2 * xu;                                                              \
+    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0; /* a tape value must never be an FMA ADDEND: ptxas then */ \
+    TAPE_ROW_FETCH(min(row + 1, row_last))         /* drops the whole stream from LDCU to vector LDC       */
+#define TAPE_ROW_POST(ROWBYTES)                                                                          \
+    S0 = ((S0 + S1) + (S2 + S3)) + q0x;                                                                  \
+    e = fma(S0, P, e);                                                                                   \
+    tape_sts(au_ + gs_delta, fma(S0, p2, tape_lds(au_ + gs_delta)));                                     \
+    TAPE_WV_UPDATES                                                                                      \
+    TAPE_ADVANCE(cp, ROWBYTES);                                                                          \
+    ++row;
+
+// One pass: adds the rows of window `pass` to (E, g).  x must already be in registers; g/E are accumulated into.
+template <int WHICH, int NV>
+__device__ __forceinline__ void tape_eval_const_pass(int pass, double (&x)[NV], double (&g)[NV], double& E, TapeCSmem<NV>& sm)
+{
+    const unsigned* rowvars = (WHICH == 3) ? c_tape_rowvars3b : c_tape_rowvars2b;
+    const unsigned* segs = (WHICH == 3) ? c_tape_csegs3b : c_tape_csegs2b;
+    const int(*cpass)[3] = (WHICH == 3) ? c_tape_cpass3b : c_tape_cpass2b;
+    const unsigned tid = threadIdx.x;
+    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
+    const unsigned gs_delta = (unsigned)sizeof(sm.xs);
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        tape_sts(xs_t + c * TAPE_COL, x[c]);
+        tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
+    }
+    tape_sts(xs_t + NV * TAPE_COL, 1.0);
+    tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
+    double e = E;
+    unsigned long long cp;                                 // .const address of the current row inside the window
+    asm volatile("mov.u64 %0, mbpol_cwin;" : "=l"(cp));
+    unsigned row = cpass[pass][1];
+    const unsigned row_last = cpass[pass + 1][1] - 1;
+    const int sg1 = cpass[pass + 1][0];
+    unsigned nu_, nw_, nv_;
+    double nxu, nxw, nxv;
+    TAPE_ROW_FETCH(row)
+    for (int sg = cpass[pass][0]; sg < sg1; ++sg) {
+        const unsigned seg = segs[sg];
+        const unsigned type = seg & 255u, nrows = seg >> 8;
+        if (WHICH == 3) {
+            TAPE3B_SEGMENT_SWITCH(type, nrows)
+        } else {
+            TAPE2B_SEGMENT_SWITCH(type, nrows)
+        }
     }
 #pragma unroll
     for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);

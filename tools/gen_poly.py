@@ -50,6 +50,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+CWINDOW = 5376        # doubles of the shared constant-bank window (see tools/gen_tape.py)
 DATA = os.path.join(ROOT, "dlpoly2-mbpol-heat_b200", "data", "mbpol_model.npz")
 OUTD = os.path.join(ROOT, "dlpoly2-mbpol-heat_b200", "csrc", "gen")
 
@@ -298,14 +299,16 @@ def emit_ptx_part(ops, loads, stores, tag, part, nv, ncoef, barrier_period):
     that is larger than the instruction cache).
     """
     name = "poly%s_part%d" % (tag, part)
-    cname = "mbpol_coef%s" % tag
+    # both coefficient tables live in the library's single constant-bank window: 2B at [0, 1153), 3B at [1153, 2316)
+    cname = "mbpol_cwin"
+    cbase = 0 if tag == "2b" else 1153
     stride = 8 * record_doubles(nv)
     L = []
     L.append("// generated by tools/gen_poly.py -- do not edit")
     L.append(".version 8.8")
     L.append(".target sm_100a")
     L.append(".address_size 64")
-    L.append(".extern .const .align 8 .f64 %s[%d];" % (cname, ncoef))
+    L.append(".extern .const .align 16 .f64 %s[%d];" % (cname, CWINDOW))
     L.append(".visible .func %s(.param .b64 %s_buf, .param .b32 %s_nb)" % (name, name, name))
     L.append("{")
     ncref = sum(1 for o in ops for a in o[1:] if a[0] == "c")
@@ -332,7 +335,7 @@ def emit_ptx_part(ops, loads, stores, tag, part, nv, ncoef, barrier_period):
         if o[0] != "c":
             return rname(o)
         kc[0] += 1
-        pre.append("ld.const.f64 %%k%d, [%s+%d];" % (kc[0], cname, 8 * o[1]))
+        pre.append("ld.const.f64 %%k%d, [%s+%d];" % (kc[0], cname, 8 * (cbase + o[1])))
         return "%%k%d" % kc[0]
 
     mn = {"fma": "fma.rn.f64", "mul": "mul.rn.f64", "add": "add.rn.f64", "mov": "mov.f64"}

@@ -34,7 +34,8 @@ import numpy as np
 import gen_poly as G
 
 OUTD = G.OUTD
-CHUNK = 1024          # doubles per staged tape chunk (8 KB)
+CHUNK = 1024          # doubles per staged tape chunk (8 KB), shared-memory tape engine
+CWINDOW = G.CWINDOW    # doubles of the constant-bank window (42 KB), constant tape engine
 NSUM = 2              # independent partial sums of the Horner accumulator S (shortens the dependent DFMA chain)
 
 
@@ -88,28 +89,37 @@ def emit_header(tag, nv, rows, types, mode):
     by_id = {t: vs for vs, t in types.items()}
     nt = len(types)
     tape, rowvars = [], []
-    chunks = []            # (first segment, first row, first tape slot)
-    segs = []              # type | nrows << 8
-    used = CHUNK + 1       # force a new chunk at the first row
     nfma = 0
     for (t, u, w, v, own, cs) in rows:
-        n = row_slots(len(cs))
-        if used + n > CHUNK:
-            chunks.append((len(segs), len(rowvars), len(tape)))
-            used = 0
-            cur_type = None
-        if cur_type != t or (segs[-1] >> 8) >= 0xffffff:
-            segs.append(t)
-            cur_type = t
-        segs[-1] += 1 << 8
-        used += n
         rowvars.append(u | (w << 8) | (v << 16))
         tape.append(own)
         tape.extend(cs)
         if len(tape) % 2:
             tape.append(-1)
         nfma += 2 * len(cs) + 9
-    chunks.append((len(segs), len(rowvars), len(tape)))
+
+    def partition(limit):
+        """Cut the (type-sorted) row list into pieces of <= limit tape slots; inside a piece, runs of equal type
+        are segments (type | nrows << 8).  Returns (segs, pieces) with pieces = (first seg, first row, first slot)."""
+        segs, pieces = [], []
+        used, pos, cur = limit + 1, 0, None
+        for i, (t, u, w, v, own, cs) in enumerate(rows):
+            n = row_slots(len(cs))
+            if used + n > limit:
+                pieces.append((len(segs), i, pos))
+                used, cur = 0, None
+            if cur != t:
+                segs.append(t)
+                cur = t
+            segs[-1] += 1 << 8
+            used += n
+            pos += n
+        assert pos == len(tape)
+        pieces.append((len(segs), len(rows), len(tape)))
+        return segs, pieces
+
+    segs, chunks = partition(CHUNK)
+    csegs, cpass = partition(CWINDOW)
     L = ["// generated by tools/gen_tape.py (%s, trie order=%s) -- do not edit" % (tag, mode), "#pragma once",
          "#define TAPE%s_NV %d" % (T, nv), "#define TAPE%s_NROWS %d" % (T, len(rows)), "#define TAPE%s_NTAPE %d" % (T, len(tape)),
          "#define TAPE%s_NSEGS %d" % (T, len(segs)), "#define TAPE%s_NCHUNKS %d" % (T, len(chunks) - 1),
@@ -118,11 +128,18 @@ def emit_header(tag, nv, rows, types, mode):
     L.append("static const unsigned TAPE%s_SEGS_HOST[%d] = {%s};" % (T, len(segs), ",".join(str(w) for w in segs)))
     L.append("static const short TAPE%s_COEFIDX_HOST[%d] = {%s};" % (T, len(tape), ",".join(str(c) for c in tape)))
     L.append("static const int TAPE%s_CHUNKS_HOST[%d][3] = {%s};" % (T, len(chunks), ",".join("{%d,%d,%d}" % c for c in chunks)))
+    L.append("// constant-bank engine: passes of <= TAPE_CWINDOW_DOUBLES tape slots")
+    L.append("#define TAPE%s_NCSEGS %d" % (T, len(csegs)))
+    L.append("#define TAPE%s_NCPASS %d" % (T, len(cpass) - 1))
+    L.append("#define TAPE_CWINDOW_DOUBLES %d" % CWINDOW)
+    L.append("static const unsigned TAPE%s_CSEGS_HOST[%d] = {%s};" % (T, len(csegs), ",".join(str(w) for w in csegs)))
+    L.append("static const int TAPE%s_CPASS_HOST[%d][3] = {%s};" % (T, len(cpass), ",".join("{%d,%d,%d}" % c for c in cpass)))
     L.append("// One counted loop per row type: TAPE_ROW_PRE loads (x_u, x_w, x_v), forms P and the first tape pair (q0x = own,")
     L.append("// q0y = first coefficient); the body accumulates S0/S1 (two partial Horner sums) and g[c] += a_c*P with static")
     L.append("// register names; TAPE_ROW_POST(bytes) adds S*P to E, updates the three dynamic gradient slots and advances the tape.")
-    L.append("#define TAPE%s_SEGMENT_SWITCH(type, nrows) switch (type) { \\" % T)
-    for t in range(nt):
+    # an if-chain, not a switch: an indirect branch (BRX) makes ptxas give up on warp-uniformity of the tape pointer
+    L.append("#define TAPE%s_SEGMENT_SWITCH(type, nrows) { \\" % T)
+    for t in range(min(nt, int(os.environ.get("TAPE_MAXTYPES", "1000")))):      # TAPE_MAXTYPES: compile-time experiments only
         vs = by_id[t]
         body, have = [], {0}
         for i, v in enumerate(vs):
@@ -130,13 +147,13 @@ def emit_header(tag, nv, rows, types, mode):
             pair, lane = slot // 2, slot % 2
             if pair not in have:
                 have.add(pair)
-                body.append("double q%dx, q%dy; TAPE_LDS_V2(q%dx, q%dy, cp, %d);" % (pair, pair, pair, pair, 16 * pair))
+                body.append("double q%dx, q%dy; TAPE_LD2(q%dx, q%dy, cp, %d);" % (pair, pair, pair, pair, 16 * pair))
             a = "q%d%s" % (pair, "xy"[lane])
             acc = "S%d" % (i % NSUM)
             body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, P, g[%d]);" % (acc, a, v, acc, v, a, v))
-        L.append("case %d: TAPE_ROW_LOOP(nrows) { TAPE_ROW_PRE(%d) %s TAPE_ROW_POST(%d) } break; \\" % (
-            t, 8 * row_slots(len(vs)), " ".join(body), 8 * row_slots(len(vs))))
-    L.append("default: break; }")
+        L.append("%sif ((type) == %d) { TAPE_ROW_LOOP(nrows) { TAPE_ROW_PRE(%d) %s TAPE_ROW_POST(%d) } } \\" % (
+            "else " if t else "", t, 8 * row_slots(len(vs)), " ".join(body), 8 * row_slots(len(vs))))
+    L.append("}")
     return "\n".join(L) + "\n", nfma, len(chunks) - 1, len(segs)
 
 
