@@ -162,7 +162,7 @@ def workload_config(box, args, nd, nt):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nw", type=int, default=32768, help="waters in the synthetic box (BASELINE configs: 4096, 32768)")
@@ -234,7 +234,6 @@ def main():
     k3.clear()
     ms = [step() for _ in range(args.steps)]
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     t_dev = torch.tensor([sum(ms) / len(ms)], dtype=torch.float64, device="cuda")
     t3 = torch.tensor([np.mean([k["k3b_ms"] for k in k3])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -273,6 +272,7 @@ def main():
         dt, res = e2e_step()
         te.append(dt)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the device-timed AND the end-to-end region
     t_e2e = torch.tensor([float(np.mean(te))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -282,6 +282,10 @@ def main():
     if rank == 0:
         nt, nd = counts["trimers"], counts["dimers"]
         peak = mb.measure_fp64_peak()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_k_trimers_traffic.json")
+        if world == 1 and args.nw == 32768 and os.path.exists(tpath):      # ncu --set full capture of the same launch
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         k3ms = float(t3.item())
         nts = counts["trimers_shard"]
         achieved = nts * mb.FLOP_PER_TRIMER / (k3ms * 1e-3) * 1e-12
@@ -293,7 +297,7 @@ def main():
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": "k_trimers", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None, "kernel_ms": k3ms,
+                             "frac": achieved / peak, "traffic": traffic, "kernel_ms": k3ms,
                              "peak_source": "measured live: independent DFMA chains (mbpol_b200_measure_fp64_peak); "
                                             "MEASURED_PEAKS.json has no FP64 entry",
                              "algorithmic_flop_per_trimer": mb.FLOP_PER_TRIMER,
