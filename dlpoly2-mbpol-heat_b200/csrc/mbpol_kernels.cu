@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mbpol_b200.h"
@@ -118,8 +119,14 @@ __global__ void k_cell_fill(int nw, const int* __restrict__ cell_id, const int* 
 //   nb3[i][*]: j != i with sqrt(r^2) <= r3f (reject: r .gt. r3f,      mbpol.f90:865-869)
 // d = O_min(i,j) - O_max(i,j), then the reference's minimum image.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sort_row(int* __restrict__ row, int n)
+// The cell fill order comes from atomics; sorting every cell's (short) member list makes the neighbour rows -- and
+// therefore the lists and the per-rank shards cut out of them -- identical on every GPU and from call to call.
+__global__ void k_sort_cells(int ncells, const int* __restrict__ cell_start, int* __restrict__ sorted)
 {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int* row = sorted + cell_start[c];
+    const int n = cell_start[c + 1] - cell_start[c];
     for (int a = 1; a < n; ++a) {
         const int v = row[a];
         int b = a - 1;
@@ -128,11 +135,14 @@ __device__ __forceinline__ void sort_row(int* __restrict__ row, int n)
     }
 }
 
+// One WARP per water: the lanes share the scan of the 27 surrounding cells; accepted partners are appended with a
+// ballot/prefix so the row order is (cell order, member order) -- deterministic.
 __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C, Grid G, const int* __restrict__ cell_start,
                              const int* __restrict__ sorted, int* __restrict__ nb2, int* __restrict__ n2, int* __restrict__ nb3,
                              int* __restrict__ n3, int* __restrict__ overflow)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     if (t >= nw) return;
     const int i = sorted[t];
     const double xi = mono[i], yi = mono[(size_t)nw + i], zi = mono[2 * (size_t)nw + i];
@@ -151,34 +161,37 @@ __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C
             for (int dx = 0; dx < cnt[0]; ++dx) {
                 const int cx = (lo[0] + dx + G.nc[0]) % G.nc[0], cy = (lo[1] + dy + G.nc[1]) % G.nc[1], cz = (lo[2] + dz + G.nc[2]) % G.nc[2];
                 const int c = (cz * G.nc[1] + cy) * G.nc[0] + cx;
-                for (int p = cell_start[c]; p < cell_start[c + 1]; ++p) {
-                    const int j = sorted[p];
-                    if (j == i) continue;
-                    const double xj = mono[j], yj = mono[(size_t)nw + j], zj = mono[2 * (size_t)nw + j];
-                    double ddx, ddy, ddz;
-                    if (i < j) { ddx = __dsub_rn(xi, xj); ddy = __dsub_rn(yi, yj); ddz = __dsub_rn(zi, zj); }
-                    else       { ddx = __dsub_rn(xj, xi); ddy = __dsub_rn(yj, yi); ddz = __dsub_rn(zj, zi); }
-                    image_vec(C, ddx, ddy, ddz);
-                    const double rsq = norm2_exact(ddx, ddy, ddz);
-                    if (j > i && !(rsq > r2f2)) {
-                        if (c2 < NB2_CAP) nb2[(size_t)i * NB2_CAP + c2] = j;
-                        ++c2;
+                const int p1 = cell_start[c + 1];
+                for (int p0 = cell_start[c]; p0 < p1; p0 += 32) {
+                    const int p = p0 + (int)lane;
+                    bool in2 = false, in3 = false;
+                    int j = -1;
+                    if (p < p1) {
+                        j = sorted[p];
+                        if (j != i) {
+                            const double xj = mono[j], yj = mono[(size_t)nw + j], zj = mono[2 * (size_t)nw + j];
+                            double ddx, ddy, ddz;
+                            if (i < j) { ddx = __dsub_rn(xi, xj); ddy = __dsub_rn(yi, yj); ddz = __dsub_rn(zi, zj); }
+                            else       { ddx = __dsub_rn(xj, xi); ddy = __dsub_rn(yj, yi); ddz = __dsub_rn(zj, zi); }
+                            image_vec(C, ddx, ddy, ddz);
+                            const double rsq = norm2_exact(ddx, ddy, ddz);
+                            in2 = j > i && !(rsq > r2f2);
+                            in3 = !(__dsqrt_rn(rsq) > mbpol_par.r3f);
+                        }
                     }
-                    if (!(__dsqrt_rn(rsq) > mbpol_par.r3f)) {
-                        if (c3 < NB3_CAP) nb3[(size_t)i * NB3_CAP + c3] = j;
-                        ++c3;
-                    }
+                    const unsigned b2 = __ballot_sync(0xffffffffu, in2), b3 = __ballot_sync(0xffffffffu, in3);
+                    const int q2 = c2 + __popc(b2 & lt), q3 = c3 + __popc(b3 & lt);
+                    if (in2 && q2 < NB2_CAP) nb2[(size_t)i * NB2_CAP + q2] = j;
+                    if (in3 && q3 < NB3_CAP) nb3[(size_t)i * NB3_CAP + q3] = j;
+                    c2 += __popc(b2);
+                    c3 += __popc(b3);
                 }
             }
-    if (c2 > NB2_CAP || c3 > NB3_CAP) atomicExch(overflow, 1);
-    c2 = min(c2, NB2_CAP);
-    c3 = min(c3, NB3_CAP);
-    n2[i] = c2;
-    n3[i] = c3;
-    // The cell fill order comes from atomics; sort the rows so that the lists (and therefore the per-rank shards cut
-    // out of them) are identical on every GPU and from call to call.
-    sort_row(nb2 + (size_t)i * NB2_CAP, c2);
-    sort_row(nb3 + (size_t)i * NB3_CAP, c3);
+    if (lane == 0) {
+        if (c2 > NB2_CAP || c3 > NB3_CAP) atomicExch(overflow, 1);
+        n2[i] = min(c2, NB2_CAP);
+        n3[i] = min(c3, NB3_CAP);
+    }
 }
 
 __global__ void k_fill_dimers(int nw, const int* __restrict__ nb2, const int* __restrict__ n2, const long long* __restrict__ off,
@@ -204,28 +217,41 @@ template <bool FILL>
 __global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* __restrict__ n3, long long* __restrict__ cnt,
                                const long long* __restrict__ off, int* __restrict__ trimers)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per centre
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     if (c >= nw) return;
     const int* row = nb3 + (size_t)c * NB3_CAP;
     const int n = n3[c];
+    const int npairs = n * (n - 1) / 2;
     long long k = 0;
     const long long base = FILL ? off[c] : 0;
-    for (int p = 0; p < n; ++p)
-        for (int q = p + 1; q < n; ++q) {
-            const int a = row[p], b = row[q];
+    for (int e0 = 0; e0 < npairs; e0 += 32) {
+        const int e = e0 + (int)lane;
+        bool emit = false;
+        int a = 0, b = 0;
+        if (e < npairs) {
+            // pair index e -> (p, q), p < q, in the order (0,1), (0,2), (1,2), (0,3), ...: q = row of the triangle
+            int q = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);
+            while (q * (q - 1) / 2 > e) --q;
+            while ((q + 1) * q / 2 <= e) ++q;
+            const int pp = e - q * (q - 1) / 2;
+            a = row[pp];
+            b = row[q];
             const bool closed = in_row(nb3 + (size_t)a * NB3_CAP, n3[a], b);
-            if (closed && !(c < a && c < b)) continue;
-            if (FILL) {
-                int t0 = c, t1 = a, t2 = b, s;
-                if (t0 > t1) { s = t0; t0 = t1; t1 = s; }
-                if (t1 > t2) { s = t1; t1 = t2; t2 = s; }
-                if (t0 > t1) { s = t0; t0 = t1; t1 = s; }
-                int* o = trimers + 3 * (base + k);
-                o[0] = t0; o[1] = t1; o[2] = t2;
-            }
-            ++k;
+            emit = !(closed && !(c < a && c < b));
         }
-    if (!FILL) cnt[c] = k;
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (FILL && emit) {
+            int t0 = c, t1 = a, t2 = b, s_;
+            if (t0 > t1) { s_ = t0; t0 = t1; t1 = s_; }
+            if (t1 > t2) { s_ = t1; t1 = t2; t2 = s_; }
+            if (t0 > t1) { s_ = t0; t0 = t1; t1 = s_; }
+            int* o = trimers + 3 * (base + k + __popc(m & lt));
+            o[0] = t0; o[1] = t1; o[2] = t2;
+        }
+        k += __popc(m);
+    }
+    if (!FILL && lane == 0) cnt[c] = k;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -965,14 +991,16 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     k_cell_index<<<gb, TB, 0, s>>>(nw, h->mono.p, h->G, h->cell_id.p, h->cell_cnt.p);
     if (int rc = scan_int(h, h->cell_cnt.p, h->cell_cnt.p, h->ncells + 1)) return rc;   // in-place exclusive scan -> cell_start
     k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->sorted.p);
-    k_neighbours<<<gb, TB, 0, s>>>(nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
+    k_sort_cells<<<(h->ncells + TB - 1) / TB, TB, 0, s>>>(h->ncells, h->cell_cnt.p, h->sorted.p);
+    const int gw = (int)(((size_t)nw * 32 + TB - 1) / TB);      // one warp per water
+    k_neighbours<<<gw, TB, 0, s>>>(nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
     k_widen<<<(nw + 1 + TB - 1) / TB, TB, 0, s>>>(nw, h->n2.p, h->n2ll.p);
     CUDA_TRY(h, cudaMemsetAsync(h->n2ll.p + nw, 0, 8, s));
     CUDA_TRY(h, cudaMemsetAsync(h->cnt3.p + nw, 0, 8, s));
     if (int rc = scan_ll(h, h->n2ll.p, h->off2.p, nw + 1)) return rc;
-    k_trimers_enum<false><<<gb, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, h->cnt3.p, nullptr, nullptr);
+    k_trimers_enum<false><<<gw, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, h->cnt3.p, nullptr, nullptr);
     if (int rc = scan_ll(h, h->cnt3.p, h->off3.p, nw + 1)) return rc;
-    h->launches += 9;
+    h->launches += 10;
     long long tot[2];
     int ovf = 0;
     CUDA_TRY(h, cudaMemcpyAsync(&tot[0], h->off2.p + nw, 8, cudaMemcpyDeviceToHost, s));
@@ -984,7 +1012,7 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     CUDA_TRY(h, h->dimers.reserve((size_t)std::max<long long>(tot[0], 1)));
     CUDA_TRY(h, h->trimers.reserve((size_t)std::max<long long>(3 * tot[1], 3)));
     k_fill_dimers<<<gb, TB, 0, s>>>(nw, h->nb2.p, h->n2.p, h->off2.p, h->dimers.p);
-    k_trimers_enum<true><<<gb, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, nullptr, h->off3.p, h->trimers.p);
+    k_trimers_enum<true><<<gw, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, nullptr, h->off3.p, h->trimers.p);
     h->launches += 2;
     CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
 
@@ -1065,10 +1093,28 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
     if (atomic_fdecomp) CUDA_TRY(h, cudaMemcpyAsync(P + 13 * n, h->out.p + 13 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, NSCAL * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    for (size_t i = 0; i < n; ++i) { fxx[i] += P[i]; fyy[i] += P[n + i]; fzz[i] += P[2 * n + i]; }
-    if (atomic_energy) for (size_t i = 0; i < n; ++i) atomic_energy[i] += P[3 * n + i];
-    if (atomic_stress) for (size_t i = 0; i < 9 * n; ++i) atomic_stress[i] += P[4 * n + i];
-    if (atomic_fdecomp) for (size_t i = 0; i < 9 * n; ++i) atomic_fdecomp[i] += P[13 * n + i];
+    // accumulate into the caller's arrays (the reference's "+=" semantics); a few host threads for the 22*mxatms adds
+    struct Job { double* dst; const double* src; size_t len; };
+    std::vector<Job> jobs = {{fxx, P, n}, {fyy, P + n, n}, {fzz, P + 2 * n, n}};
+    if (atomic_energy) jobs.push_back({atomic_energy, P + 3 * n, n});
+    if (atomic_stress) jobs.push_back({atomic_stress, P + 4 * n, 9 * n});
+    if (atomic_fdecomp) jobs.push_back({atomic_fdecomp, P + 13 * n, 9 * n});
+    size_t total = 0;
+    for (auto& j : jobs) total += j.len;
+    const unsigned nth = total < (1u << 18) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    auto work = [&](unsigned t) {
+        for (auto& j : jobs) {
+            const size_t a = j.len * t / nth, b = j.len * (t + 1) / nth;
+            for (size_t i = a; i < b; ++i) j.dst[i] += j.src[i];
+        }
+    };
+    if (nth == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nth; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+    }
     const double* sc = P + 22 * n;
     if (eng2) *eng2 += sc[S_ENG2];
     if (vir2) *vir2 += sc[S_VIR2];
