@@ -81,9 +81,39 @@ __device__ __forceinline__ double switch_fn(double r, double ri, double rf, doub
 // local memory.  ENGINE 1: coefficient-tape interpreter (tools/gen_tape.py, mbpol_tape.cuh); needs the whole CTA.
 // ---------------------------------------------------------------------------------------------------------
 struct PolyCtx {
-    void* smem;              // TapeSmem<NV>* for ENGINE 1
+    void* smem;              // TapeSmem<NV>* (ENGINE 1) / TapeCSmem<NV>* (ENGINE 2)
     const double* tape;      // device tape for ENGINE 1
+    // ENGINE 2 (constant-window passes): partial (g, E) of cluster `idx` of `count` lives in gbuf[c * count + idx]
+    double* gbuf;
+    long long idx, count;
+    bool first, last, valid;
 };
+
+// engine 2 row loops: separate ptxas units (mbpol_tape_cpass.cu)
+extern "C" __device__ void mbpol_tape3b_cpass(double* rec, TapeCSmem<36>* sm);
+extern "C" __device__ void mbpol_tape2b_cpass(double* rec, TapeCSmem<31>* sm);
+
+// one constant-window pass on a record [x(NV) | E | g(NV)]; returns true when the polynomial is complete
+template <int NV>
+__device__ __forceinline__ bool cpass_step(double* rec, const PolyCtx& ctx)
+{
+    if (ctx.first) {
+#pragma unroll
+        for (int c = NV; c < 2 * NV + 1; ++c) rec[c] = 0.0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) rec[NV + 1 + c] = ctx.gbuf[(size_t)c * ctx.count + ctx.idx];
+        rec[NV] = ctx.gbuf[(size_t)NV * ctx.count + ctx.idx];
+    }
+    if (NV == 36) mbpol_tape3b_cpass(rec, reinterpret_cast<TapeCSmem<36>*>(ctx.smem));
+    else mbpol_tape2b_cpass(rec, reinterpret_cast<TapeCSmem<31>*>(ctx.smem));
+    if (!ctx.last && ctx.valid) {
+#pragma unroll
+        for (int c = 0; c < NV; ++c) ctx.gbuf[(size_t)c * ctx.count + ctx.idx] = rec[NV + 1 + c];
+        ctx.gbuf[(size_t)NV * ctx.count + ctx.idx] = rec[NV];
+    }
+    return ctx.last;
+}
 
 // =========================================================================================================
 // 3B
@@ -129,22 +159,27 @@ __device__ __forceinline__ void trimer_finish(const double* xv, const double* gp
     E = s * Epoly;
 }
 
+// returns false when the polynomial is not complete yet (engine 2, not the last pass): E and cv are then undefined
 template <int ENGINE>
-__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+__device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
 {
-    double xv[ENGINE ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE ? 36 : 1];
-    double* gp = ENGINE ? gp_ : xv + 37;      // ENGINE 0: x and g live in the per-thread record (local memory)
+    double xv[ENGINE == 1 ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE == 1 ? 36 : 1];
+    double* gp = ENGINE == 1 ? gp_ : xv + 37;      // ENGINE 0/2: x and g live in the per-thread record (local memory)
     double rinv[36];
     trimer_variables(r, xv, rinv);
     double Epoly;
     if (ENGINE == 0) {
         POLY3B_CALL_ALL(xv, 1u);
         Epoly = xv[36];
+    } else if (ENGINE == 2) {
+        if (!cpass_step<36>(xv, ctx)) return false;
+        Epoly = xv[36];
     } else {
         tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
                          *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
     }
     trimer_finish(xv, gp, Epoly, rinv, E, cv);
+    return true;
 }
 
 // gradient on the 9 atoms from cv:  g[3*atom + c]
@@ -226,12 +261,12 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     if (fm)
         for (int i = 0; i < 108; ++i) fm[i] = 0.0;
     const bool inside = !(rOO > mbpol_par.r2f);
-    if (ENGINE == 0 && !inside) return false;           // the tape engine has CTA barriers: every thread walks on
+    if (ENGINE != 1 && !inside && (ENGINE == 0 || ctx.last)) return false;   // engine 1 has CTA barriers: every thread walks on
     lonepair_sites(xc + 0, xc + 18, xc + 21);
     lonepair_sites(xc + 9, xc + 24, xc + 27);
 
-    double xv[ENGINE ? 31 : POLY2B_RECORD_DOUBLES], gp_[ENGINE ? 31 : 1];
-    double* gp = ENGINE ? gp_ : xv + 32;
+    double xv[ENGINE == 1 ? 31 : POLY2B_RECORD_DOUBLES], gp_[ENGINE == 1 ? 31 : 1];
+    double* gp = ENGINE == 1 ? gp_ : xv + 32;
     double gfac[31];    // dv/dr / r : the variable's gradient is gfac * (r_a - r_b)
 #pragma unroll
     for (int n = 0; n < 31; ++n) {
@@ -254,6 +289,9 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     double Epoly;
     if (ENGINE == 0) {
         POLY2B_CALL_ALL(xv, 1u);
+        Epoly = xv[31];
+    } else if (ENGINE == 2) {
+        if (!cpass_step<31>(xv, ctx)) return false;
         Epoly = xv[31];
     } else {
         tape_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,

@@ -406,71 +406,25 @@ template <int ENGINE>
 __global__ void __launch_bounds__(256, 1)
 k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
           const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-          const double* __restrict__ tape)
+          const double* __restrict__ tape, double* __restrict__ gbuf, bool first, bool last)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape};
     const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t0_ < ntri;
-    const long long t = valid ? t0_ : ntri - 1;          // idle lanes shadow the last trimer (tape engine: CTA barriers)
+    // idle lanes shadow the last trimer: engine 1 has CTA barriers, engine 2 needs thread-independent control flow
+    const long long t = valid ? t0_ : ntri - 1;
+    const PolyCtx ctx{dyn_smem, tape, gbuf, t, ntri, first, last, valid};
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
-    if (ENGINE == 1 || valid) {
+    if (ENGINE != 0 || valid) {
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
         double r[27];
         trimer_geometry(nw, mono, C, mi, mj, mk, r);
         double E, cv[36];
-        trimer_eval<ENGINE>(r, E, cv, ctx);
+        const bool done = trimer_eval<ENGINE>(r, E, cv, ctx);
         const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
-        if (valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
+        if (done && valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
     }
-    trimer_block_scalars(sc, O);
-}
-
-// Engine 2 (constant-bank tape): one launch per constant window.  gbuf[c * ntri + t], c = 0..36: partial (g[36], E)
-// of trimer t between the passes (coalesced SoA in HBM).  The last pass runs the chain rule and the scatter.
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(256, 1)
-k_trimers_cpass(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-                const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-                int pass, double* __restrict__ gbuf)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    // no thread-dependent control flow around the row loops: the tape index must stay provably warp-uniform so that the
-    // coefficient loads compile to LDCU (uniform datapath).  Idle lanes shadow the last trimer and skip the stores.
-    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t0_ < ntri;
-    const long long t = valid ? t0_ : ntri - 1;
-    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    {
-        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
-        double r[27];
-        trimer_geometry(nw, mono, C, mi, mj, mk, r);
-        double xv[36], rinv[36], gp[36], Epoly;
-        trimer_variables(r, xv, rinv);
-        if (FIRST) {
-#pragma unroll
-            for (int c = 0; c < 36; ++c) gp[c] = 0.0;
-            Epoly = 0.0;
-        } else {
-#pragma unroll
-            for (int c = 0; c < 36; ++c) gp[c] = gbuf[(size_t)c * ntri + t];
-            Epoly = gbuf[(size_t)36 * ntri + t];
-        }
-        tape_eval_const_pass<3, 36>(pass, xv, gp, Epoly, *reinterpret_cast<TapeCSmem<36>*>(dyn_smem));
-        if (!LAST) {
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < 36; ++c) gbuf[(size_t)c * ntri + t] = gp[c];
-                gbuf[(size_t)36 * ntri + t] = Epoly;
-            }
-        } else {
-            double E, cv[36];
-            trimer_finish(xv, gp, Epoly, rinv, E, cv);
-            const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};
-            if (valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
-        }
-    }
-    if (LAST) trimer_block_scalars(sc, O);
+    if (ENGINE != 2 || last) trimer_block_scalars(sc, O);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -480,15 +434,15 @@ template <int ENGINE>
 __global__ void __launch_bounds__(256, 1)
 k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-         const double* __restrict__ tape)
+         const double* __restrict__ tape, double* __restrict__ gbuf, bool first, bool last)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape};
     const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t0_ < ndim;
+    bool valid = t0_ < ndim;
     const long long t = valid ? t0_ : ndim - 1;
+    const PolyCtx ctx{dyn_smem, tape, gbuf, t, ndim, first, last, valid};
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ENGINE == 1 || valid) {
+    if (ENGINE != 0 || valid) {
         const int mi = dim[t].x, mj = dim[t].y;
         double wi[9], wj[9], w[18];
 #pragma unroll
@@ -511,10 +465,10 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
         double E, g[18];
         double fm[108];
         const bool want_s = (flags & MBPOL_B200_WANT_ATOMIC_STRESS) != 0;
-        dimer_eval<ENGINE>(w, E, g, want_s ? fm : nullptr, ctx);
+        const bool done = dimer_eval<ENGINE>(w, E, g, want_s ? fm : nullptr, ctx) || ENGINE != 2;
         const double eu = MBPOL_ENGUNIT;
         const int o[2] = {list[3 * mi], list[3 * mj]};
-        if (valid) {
+        if (valid && done && (ENGINE != 2 || last)) {
         sc[0] = E * eu;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
@@ -563,6 +517,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
         }
         }   // valid
     }
+    if (ENGINE == 2 && !last) return;
     double v2[2] = {sc[0], sc[1]};
     block_reduce_add<2>(v2, O.scal + S_ENG2);
     __syncthreads();
@@ -608,7 +563,7 @@ template <int ENGINE>
 __global__ void __launch_bounds__(256, 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape};
+    const PolyCtx ctx{dyn_smem, tape, nullptr, 0, 0, true, true, true};
     const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
     if (ENGINE == 0 && t0_ >= n) return;
     const int t = min(t0_, n - 1);
@@ -626,7 +581,7 @@ template <int ENGINE>
 __global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape};
+    const PolyCtx ctx{dyn_smem, tape, nullptr, 0, 0, true, true, true};
     const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
     if (ENGINE == 0 && t0_ >= n) return;
     const int t = min(t0_, n - 1);
@@ -688,6 +643,18 @@ cudaError_t load_window(const double* dsrc, size_t ndoubles, cudaStream_t s)
 {
     return cudaMemcpyToSymbolAsync(mbpol_cwin, dsrc, ndoubles * 8, 0, cudaMemcpyDeviceToDevice, s);
 }
+// engine 2: window = [TapeCPassHeader (16 B) | tape slots of pass p]
+TapeCPassHeader* g_hdr2b[16] = {nullptr};
+TapeCPassHeader* g_hdr3b[16] = {nullptr};
+cudaError_t load_pass_window(int device, int which, int p, cudaStream_t s)
+{
+    const int(*tab)[3] = which == 3 ? TAPE3B_CPASS_HOST : TAPE2B_CPASS_HOST;
+    const TapeCPassHeader* hdr = (which == 3 ? g_hdr3b : g_hdr2b)[device] + p;
+    const double* tape = (which == 3 ? g_tape3b : g_tape2b)[device] + tab[p][2];
+    cudaError_t e = cudaMemcpyToSymbolAsync(mbpol_cwin, hdr, sizeof(TapeCPassHeader), 0, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(mbpol_cwin, tape, (size_t)(tab[p + 1][2] - tab[p][2]) * 8, 16, cudaMemcpyDeviceToDevice, s);
+}
 cudaError_t load_coef_window(int device, cudaStream_t s) { return load_window(g_coefwin[device], MBPOL_NCOEF2B + MBPOL_NCOEF3B, s); }
 
 // polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory, 2 = coefficient tape in
@@ -703,7 +670,7 @@ int default_engine()
     if (e && std::string(e) == "ctape") return 2;
     return MBPOL_DEFAULT_ENGINE;
 }
-constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM3C = sizeof(TapeCSmem<36>);
+constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM2C = sizeof(TapeCSmem<31>), SMEM3C = sizeof(TapeCSmem<36>);
 
 template <class K>
 cudaError_t allow_smem(K kernel, size_t bytes)
@@ -758,6 +725,14 @@ int upload_constants(int device)
         if (cudaMemcpy(d2, t2.data(), t2.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
         if (cudaMemcpy(d3, t3.data(), t3.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
         g_tape2b[device] = d2; g_tape3b[device] = d3;
+        std::vector<TapeCPassHeader> h2(TAPE2B_NCPASS), h3(TAPE3B_NCPASS);
+        for (int p = 0; p < TAPE2B_NCPASS; ++p)
+            h2[p] = {TAPE2B_CPASS_HOST[p][0], TAPE2B_CPASS_HOST[p + 1][0], (unsigned)TAPE2B_CPASS_HOST[p][1], (unsigned)TAPE2B_CPASS_HOST[p + 1][1] - 1u};
+        for (int p = 0; p < TAPE3B_NCPASS; ++p)
+            h3[p] = {TAPE3B_CPASS_HOST[p][0], TAPE3B_CPASS_HOST[p + 1][0], (unsigned)TAPE3B_CPASS_HOST[p][1], (unsigned)TAPE3B_CPASS_HOST[p + 1][1] - 1u};
+        if (cudaMalloc(&g_hdr2b[device], h2.size() * sizeof(TapeCPassHeader)) != cudaSuccess || cudaMalloc(&g_hdr3b[device], h3.size() * sizeof(TapeCPassHeader)) != cudaSuccess) return 1;
+        if (cudaMemcpy(g_hdr2b[device], h2.data(), h2.size() * sizeof(TapeCPassHeader), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        if (cudaMemcpy(g_hdr3b[device], h3.data(), h3.size() * sizeof(TapeCPassHeader), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
     }
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(c_tape_csegs2b, TAPE2B_CSEGS_HOST, sizeof(TAPE2B_CSEGS_HOST)) != cudaSuccess) return 1;
@@ -876,8 +851,7 @@ int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle
     auto* h = new mbpol_b200_handle;
     h->device = device; h->nw = nttm2 / 3; h->flags = flags; h->engine = default_engine();
     if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
-        allow_smem(k_trimers_cpass<true, false>, SMEM3C) != cudaSuccess || allow_smem(k_trimers_cpass<false, false>, SMEM3C) != cudaSuccess ||
-        allow_smem(k_trimers_cpass<false, true>, SMEM3C) != cudaSuccess || allow_smem(k_trimers_cpass<true, true>, SMEM3C) != cudaSuccess) {
+        allow_smem(k_dimers<2>, SMEM2C) != cudaSuccess || allow_smem(k_trimers<2>, SMEM3C) != cudaSuccess) {
         delete h;
         return MBPOL_B200_ECUDA;
     }
@@ -1024,10 +998,21 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     if (h->nd_shard > 0) {
         const unsigned gd = (unsigned)((h->nd_shard + 255) / 256);
-        if (h->engine) k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
-        else {
+        const int2* dl = h->dimers.p + d0;
+        if (h->engine == 2) {
+            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * std::max(h->nt_shard, h->nd_shard)));
+            for (int p = 0; p < TAPE2B_NCPASS; ++p) {
+                CUDA_TRY(h, load_pass_window(h->device, 2, p, s));
+                k_dimers<2><<<gd, 256, SMEM2C, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, h->gbuf.p,
+                                                    p == 0, p == TAPE2B_NCPASS - 1);
+                ++h->launches;
+            }
+            --h->launches;
+        } else if (h->engine == 1) {
+            k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device], nullptr, true, true);
+        } else {
             CUDA_TRY(h, load_coef_window(h->device, s));
-            k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, h->dimers.p + d0, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+            k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, nullptr, true, true);
         }
         ++h->launches;
     }
@@ -1036,25 +1021,19 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
         const unsigned gt = (unsigned)((h->nt_shard + 255) / 256);
         const int* tl = h->trimers.p + 3 * t0;
         if (h->engine == 2) {
-            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * h->nt_shard));
+            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * std::max(h->nt_shard, h->nd_shard)));
             for (int p = 0; p < TAPE3B_NCPASS; ++p) {
-                const int tb = TAPE3B_CPASS_HOST[p][2], te = TAPE3B_CPASS_HOST[p + 1][2];
-                CUDA_TRY(h, load_window(g_tape3b[h->device] + tb, te - tb, s));
-                const bool first = p == 0, last = p == TAPE3B_NCPASS - 1;
-#define CPASS_LAUNCH(F, L) k_trimers_cpass<F, L><<<gt, 256, SMEM3C, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, p, h->gbuf.p)
-                if (first && last) CPASS_LAUNCH(true, true);
-                else if (first) CPASS_LAUNCH(true, false);
-                else if (last) CPASS_LAUNCH(false, true);
-                else CPASS_LAUNCH(false, false);
-#undef CPASS_LAUNCH
+                CUDA_TRY(h, load_pass_window(h->device, 3, p, s));
+                k_trimers<2><<<gt, 256, SMEM3C, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, h->gbuf.p,
+                                                     p == 0, p == TAPE3B_NCPASS - 1);
                 ++h->launches;
             }
             --h->launches;
         } else if (h->engine == 1) {
-            k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
+            k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device], nullptr, true, true);
         } else {
             CUDA_TRY(h, load_coef_window(h->device, s));
-            k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr);
+            k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, nullptr, true, true);
         }
         ++h->launches;
     }
@@ -1219,7 +1198,7 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
         if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); }
         else ok(load_coef_window(device, 0));
         if (nat3 == 18) {
-            if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
+            if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);   // engine 2 -> 1 here
             else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
         } else {
             if (eng) k_eval_trimers<1><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);

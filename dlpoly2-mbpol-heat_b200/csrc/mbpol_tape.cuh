@@ -158,6 +158,12 @@ extern __constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
 extern __constant__ int c_tape_cpass2b[TAPE2B_NCPASS + 1][3];
 extern __constant__ int c_tape_cpass3b[TAPE3B_NCPASS + 1][3];
 
+// Head of every constant window (16 bytes = two tape slots): the bounds of the pass.  Read from FIXED constant-bank
+// addresses so that ptxas can prove the loop trip counts warp-uniform (a function argument or a table lookup is not enough:
+// every tape load then falls from LDCU to the vector LDC path).
+struct TapeCPassHeader { int sg0, sg1; unsigned row0, row_last; };
+#define TAPE_CWINDOW_PAYLOAD (TAPE_CWINDOW_DOUBLES - 2)
+
 template <int NV>
 struct TapeCSmem {
     double xs[NV + 1][TAPE_BS];
@@ -196,13 +202,16 @@ struct TapeCSmem {
     TAPE_ADVANCE(cp, ROWBYTES);                                                                          \
     ++row;
 
-// One pass: adds the rows of window `pass` to (E, g).  x must already be in registers; g/E are accumulated into.
+// One pass: adds the rows [row0, row_last] = segments [sg0, sg1) of one constant window to (E, g).  x must already be in
+// registers; g/E are accumulated into.  The bounds MUST arrive as kernel parameters: when they are looked up from a
+// table (even a constant-memory one indexed by a kernel parameter) ptxas no longer proves the loop trip counts
+// warp-uniform and moves every tape load from LDCU (uniform datapath) to the vector LDC path.
 template <int WHICH, int NV>
-__device__ __forceinline__ void tape_eval_const_pass(int pass, double (&x)[NV], double (&g)[NV], double& E, TapeCSmem<NV>& sm)
+__device__ __forceinline__ void tape_eval_const_pass(int sg0, int sg1, unsigned row0, unsigned row_last, double (&x)[NV], double (&g)[NV],
+                                                     double& E, TapeCSmem<NV>& sm)
 {
     const unsigned* rowvars = (WHICH == 3) ? c_tape_rowvars3b : c_tape_rowvars2b;
     const unsigned* segs = (WHICH == 3) ? c_tape_csegs3b : c_tape_csegs2b;
-    const int(*cpass)[3] = (WHICH == 3) ? c_tape_cpass3b : c_tape_cpass2b;
     const unsigned tid = threadIdx.x;
     const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
     const unsigned gs_delta = (unsigned)sizeof(sm.xs);
@@ -214,15 +223,13 @@ __device__ __forceinline__ void tape_eval_const_pass(int pass, double (&x)[NV], 
     tape_sts(xs_t + NV * TAPE_COL, 1.0);
     tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
     double e = E;
-    unsigned long long cp;                                 // .const address of the current row inside the window
-    asm volatile("mov.u64 %0, mbpol_cwin;" : "=l"(cp));
-    unsigned row = cpass[pass][1];
-    const unsigned row_last = cpass[pass + 1][1] - 1;
-    const int sg1 = cpass[pass + 1][0];
+    // .const address of the current row; the first two slots of the window hold the pass bounds (see TapeCPassHeader)
+    unsigned long long cp = (unsigned long long)__cvta_generic_to_constant(mbpol_cwin) + 16;
+    unsigned row = row0;
     unsigned nu_, nw_, nv_;
     double nxu, nxw, nxv;
     TAPE_ROW_FETCH(row)
-    for (int sg = cpass[pass][0]; sg < sg1; ++sg) {
+    for (int sg = sg0; sg < sg1; ++sg) {
         const unsigned seg = segs[sg];
         const unsigned type = seg & 255u, nrows = seg >> 8;
         if (WHICH == 3) {

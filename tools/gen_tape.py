@@ -119,7 +119,7 @@ def emit_header(tag, nv, rows, types, mode):
         return segs, pieces
 
     segs, chunks = partition(CHUNK)
-    csegs, cpass = partition(CWINDOW)
+    csegs, cpass = partition(CWINDOW - 2)      # two slots of every window hold the pass header
     L = ["// generated by tools/gen_tape.py (%s, trie order=%s) -- do not edit" % (tag, mode), "#pragma once",
          "#define TAPE%s_NV %d" % (T, nv), "#define TAPE%s_NROWS %d" % (T, len(rows)), "#define TAPE%s_NTAPE %d" % (T, len(tape)),
          "#define TAPE%s_NSEGS %d" % (T, len(segs)), "#define TAPE%s_NCHUNKS %d" % (T, len(chunks) - 1),
