@@ -90,6 +90,35 @@ def mbpol_init(nttm2, flags=DEFAULT_FLAGS, device=-1):
     return Handle(ptr, int(nttm2), int(flags))
 
 
+def mbpol_init_batched(nttm2, nbeads, flags=DEFAULT_FLAGS, device=-1):
+    """Bead-batched handle (PIMD/CMD: nbeads independent replicas of the same topology, multibead.f90:25-93)."""
+    lib = load_library()
+    ptr = C.c_void_p()
+    rc = lib.mbpol_b200_init_batched(C.c_int(int(nttm2)), C.c_int(int(nbeads)), C.c_int(int(device)), C.c_int(int(flags)), C.byref(ptr))
+    if rc:
+        raise MBPolError("mbpol_b200_init_batched failed with status %d (4 = no sm_100 GPU, 2 = CUDA error)" % rc)
+    h = Handle(ptr, int(nttm2), int(flags))
+    h.nbeads = int(nbeads)
+    return h
+
+
+def mbpol_forces_batched(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, fxx, fyy, fzz, atomic_energy=None, atomic_stress=None,
+                         atomic_fdecomp=None, vxx=None, vyy=None, vzz=None):
+    """All beads in one call: coordinate / force / per-atom arrays are [nbeads, mxatms] (C order); returns per-bead scalars."""
+    nb = h.nbeads
+    assert xxx.shape[0] == nb and xxx.flags.c_contiguous
+    mxatms = xxx.shape[1]
+    sc = [np.zeros(nb) for _ in range(4)]
+    stress, jflux = np.zeros((nb, 9)), np.zeros((nb, 9))
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    rc = load_library().mbpol_b200_forces_batched(
+        h.ptr, C.c_int(nb), C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32), C.c_int(mxatms),
+        _p(xxx), _p(yyy), _p(zzz), _p(fxx), _p(fyy), _p(fzz), _p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(stress),
+        _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz), _p(jflux))
+    _check(h, rc, "mbpol_b200_forces_batched")
+    return {"eng2": sc[0], "vir2": sc[1], "eng3": sc[2], "vir3": sc[3], "stress": stress, "jflux": jflux}
+
+
 def mbpol_fini(h):
     """mbpol.f90:89-94."""
     if h.ptr:

@@ -48,7 +48,8 @@ enum { S_ENG2 = 0, S_VIR2 = 1, S_ENG3 = 2, S_VIR3 = 3, S_STRESS = 4, S_JFLUX = 1
 
 struct OutPtrs {      // views into the packed output buffer
     double *fx, *fy, *fz, *aeng, *astress, *afd, *scal;
-    int mxatms;
+    int mxatms;       // all beads: nbeads * mxb
+    int nwb, mxb;     // waters / atoms per bead (bead-batched calls; one bead otherwise); scalars of bead b at scal + b*NSCAL
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -80,7 +81,7 @@ __global__ void k_gather_image(int nw, const int* __restrict__ list, const doubl
 // partners within either cutoff sit in the 27 surrounding cells.  The grid is only a candidate filter: membership is
 // decided by the exact predicates in k_neighbours.
 // ---------------------------------------------------------------------------------------------------------
-struct Grid { int nc[3]; double rc[9]; };
+struct Grid { int nc[3]; double rc[9]; int nwb, ncb; };   // nwb waters and ncb cells per bead: beads never see each other
 
 __device__ __forceinline__ int cell_of(const Grid& G, double x, double y, double z, int* cxyz)
 {
@@ -99,7 +100,7 @@ __global__ void k_cell_index(int nw, const double* __restrict__ mono, Grid G, in
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nw) return;
-    const int c = cell_of(G, mono[m], mono[(size_t)nw + m], mono[2 * (size_t)nw + m], nullptr);
+    const int c = (m / G.nwb) * G.ncb + cell_of(G, mono[m], mono[(size_t)nw + m], mono[2 * (size_t)nw + m], nullptr);
     cell_id[m] = c;
     atomicAdd(&cell_count[c], 1);
 }
@@ -160,7 +161,7 @@ __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C
         for (int dy = 0; dy < cnt[1]; ++dy)
             for (int dx = 0; dx < cnt[0]; ++dx) {
                 const int cx = (lo[0] + dx + G.nc[0]) % G.nc[0], cy = (lo[1] + dy + G.nc[1]) % G.nc[1], cz = (lo[2] + dz + G.nc[2]) % G.nc[2];
-                const int c = (cz * G.nc[1] + cy) * G.nc[0] + cx;
+                const int c = (i / G.nwb) * G.ncb + (cz * G.nc[1] + cy) * G.nc[0] + cx;
                 const int p1 = cell_start[c + 1];
                 for (int p0 = cell_start[c]; p0 < p1; p0 += 32) {
                     const int p = p0 + (int)lane;
@@ -281,6 +282,28 @@ __device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* dst)
     }
 }
 
+// scalars are kept per bead: reduce over the block when all its clusters belong to one bead (always, except at the
+// few blocks that straddle a bead boundary of a bead-batched call), else one atomic per thread
+template <int NV>
+__device__ __forceinline__ void block_reduce_add_bead(double (&v)[NV], double* scal, int slot, int bead /* < 0: idle lane */)
+{
+    __shared__ int bead0;
+    if (threadIdx.x == 0) bead0 = bead;          // thread 0 of a launched block always owns a cluster
+    __syncthreads();
+    const int b0 = bead0;
+    if (__syncthreads_and(bead < 0 || bead == b0)) {
+        block_reduce_add<NV>(v, scal + (size_t)b0 * NSCAL + slot);
+    } else if (bead >= 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) atomicAdd(scal + (size_t)bead * NSCAL + slot + k, v[k]);
+    }
+    __syncthreads();
+}
+
+// per-atom 3x3 tensors are stored bead-major, [nbeads][9][mxb]: component q of (0-based, all-bead) atom `atom` sits at
+// base + tensor_base(atom) + mxb*q -- for one bead this is the Fortran layout atomic_stress(mxatms,3,3)
+__device__ __forceinline__ size_t tensor_base(const OutPtrs& O, int atom) { return (size_t)atom + (size_t)(atom / O.mxb) * 8 * O.mxb; }
+
 // per-atom force-decomposition tensor W (heatcurrent.f90:529-533, 703-728):
 //   W_i(a,b) += (n*x_i - sum_j x_j)_a^raw * f_b ,  f = -g_i*engunit/n
 __device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, const double* xraw_i, const double* xsum, int n,
@@ -290,7 +313,7 @@ __device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, cons
     for (int a = 0; a < 3; ++a) {
         const double ra = n * xraw_i[a] - xsum[a];
 #pragma unroll
-        for (int b = 0; b < 3; ++b) atomicAdd(O.afd + atom + (size_t)O.mxatms * (a + 3 * b), ra * f[b]);
+        for (int b = 0; b < 3; ++b) atomicAdd(O.afd + tensor_base(O, atom) + (size_t)O.mxb * (a + 3 * b), ra * f[b]);
     }
 }
 
@@ -382,10 +405,10 @@ __device__ __forceinline__ void trimer_scatter(const double (&r)[27], double E, 
 #pragma unroll
             for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
         }
-        const size_t n = O.mxatms;
+        const size_t n = O.mxb;
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
-            double* p = O.astress + o[a / 3] - 1 + (a % 3);
+            double* p = O.astress + tensor_base(O, o[a / 3] - 1 + (a % 3));
             atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
             atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
             atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
@@ -393,13 +416,12 @@ __device__ __forceinline__ void trimer_scatter(const double (&r)[27], double E, 
     }
 }
 
-__device__ __forceinline__ void trimer_block_scalars(double (&sc)[8], const OutPtrs& O)
+__device__ __forceinline__ void trimer_block_scalars(double (&sc)[8], const OutPtrs& O, int bead)
 {
     double v2[2] = {sc[0], sc[1]};
-    block_reduce_add<2>(v2, O.scal + S_ENG3);
-    __syncthreads();
+    block_reduce_add_bead<2>(v2, O.scal, S_ENG3, bead);
     double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
-    block_reduce_add<9>(st, O.scal + S_STRESS);
+    block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
 }
 
 template <int ENGINE>
@@ -415,8 +437,10 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
     const long long t = valid ? t0_ : ntri - 1;
     const PolyCtx ctx{dyn_smem, tape, gbuf, t, ntri, first, last, valid};
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
+    int bead = -1;
     if (ENGINE != 0 || valid) {
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
+        if (valid) bead = mi / O.nwb;
         double r[27];
         trimer_geometry(nw, mono, C, mi, mj, mk, r);
         double E, cv[36];
@@ -424,7 +448,7 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
         const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
         if (done && valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
     }
-    if (ENGINE != 2 || last) trimer_block_scalars(sc, O);
+    if (ENGINE != 2 || last) trimer_block_scalars(sc, O, bead);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -442,8 +466,10 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
     const long long t = valid ? t0_ : ndim - 1;
     const PolyCtx ctx{dyn_smem, tape, gbuf, t, ndim, first, last, valid};
     double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int bead = -1;
     if (ENGINE != 0 || valid) {
         const int mi = dim[t].x, mj = dim[t].y;
+        if (valid) bead = mi / O.nwb;
         double wi[9], wj[9], w[18];
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -501,7 +527,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
             }
         }
         if (want_s) {   // mbpol.f90:558-579: S_i(a,b) = 1/2*eu*sum_{j != i} (r_i - r_j)_a * FM[i][j]_b  (FM is NOT antisymmetric)
-            const size_t n = O.mxatms;
+            const size_t n = O.mxb;
             for (int i = 0; i < 6; ++i) {
                 double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 for (int j = 0; j < 6; ++j) {
@@ -511,7 +537,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
                         for (int b = 0; b < 3; ++b) S[a + 3 * b] += ra_ * fm[18 * i + 3 * j + b];
                     }
                 }
-                double* p = O.astress + o[i / 3] - 1 + (i % 3);
+                double* p = O.astress + tensor_base(O, o[i / 3] - 1 + (i % 3));
                 for (int q = 0; q < 9; ++q) atomicAdd(p + n * q, 0.5 * eu * S[q]);
             }
         }
@@ -519,41 +545,43 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
     }
     if (ENGINE == 2 && !last) return;
     double v2[2] = {sc[0], sc[1]};
-    block_reduce_add<2>(v2, O.scal + S_ENG2);
-    __syncthreads();
+    block_reduce_add_bead<2>(v2, O.scal, S_ENG2, bead);
     double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
-    block_reduce_add<9>(st, O.scal + S_STRESS);
+    block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // K5: heat-flux contractions over the atoms of THIS shard's partial sums (linear, so partials add up)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_flux(int natoms_real, OutPtrs O, const double* __restrict__ vx, const double* __restrict__ vy,
+__global__ void k_flux(OutPtrs O, const double* __restrict__ vx, const double* __restrict__ vy,
                        const double* __restrict__ vz, int flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double j[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (i < natoms_real) {
+    // the O/H atoms of every bead; compute_heat_flux2 loops 1..3*mxatms/4 (heatcurrent.f90:710)
+    const bool in_range = i < O.mxatms;
+    const int bead = in_range ? i / O.mxb : -1;
+    if (in_range && (i % O.mxb) < 3 * O.nwb) {
         const double v[3] = {vx[i], vy[i], vz[i]};
-        const size_t n = O.mxatms;
+        const size_t n = O.mxb;
         if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
             const double e = O.aeng[i];
             j[0] = e * v[0]; j[1] = e * v[1]; j[2] = e * v[2];
         }
         if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {   // compute_heat_flux reads the upper triangle only (heatcurrent.f90:475-480)
-            const double* s = O.astress + i;
+            const double* s = O.astress + tensor_base(O, i);
             const double s11 = s[0], s12 = s[n * 3], s13 = s[n * 6], s22 = s[n * 4], s23 = s[n * 7], s33 = s[n * 8];
             j[3] = s11 * v[0] + s12 * v[1] + s13 * v[2];
             j[4] = s12 * v[0] + s22 * v[1] + s23 * v[2];
             j[5] = s13 * v[0] + s23 * v[1] + s33 * v[2];
         }
         if (flags & MBPOL_B200_WANT_FDECOMP) {
-            const double* w = O.afd + i;
+            const double* w = O.afd + tensor_base(O, i);
 #pragma unroll
             for (int a = 0; a < 3; ++a) j[6 + a] = w[n * (a + 0)] * v[0] + w[n * (a + 3)] * v[1] + w[n * (a + 6)] * v[2];
         }
     }
-    block_reduce_add<9>(j, O.scal + S_JFLUX);
+    block_reduce_add_bead<9>(j, O.scal, S_JFLUX, bead);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -780,6 +808,7 @@ struct DevBuf {
 
 struct mbpol_b200_handle {
     int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1, engine = 1;
+    int nbeads = 1, nwb = 0, mxb = 0;      // bead-batched calls: nw = nbeads*nwb waters, mxatms = nbeads*mxb atoms
     int mxatms = 0, imcon = 0;
     bool have_vel = false, uploaded = false;
     std::string err;
@@ -794,17 +823,18 @@ struct mbpol_b200_handle {
     DevBuf<long long> off2, off3, cnt3, n2ll;
     DevBuf<char> scan_tmp;
     std::vector<double> host_out;
+    std::vector<int> host_list;
     double* pinned = nullptr;
     size_t pinned_cap = 0;
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
     float ms[4] = {0, 0, 0, 0};
-    size_t out_count() const { return (size_t)22 * mxatms + NSCAL; }
+    size_t out_count() const { return (size_t)22 * mxatms + (size_t)NSCAL * nbeads; }
     OutPtrs views()
     {
         OutPtrs O;
         const size_t n = mxatms;
         O.fx = out.p; O.fy = out.p + n; O.fz = out.p + 2 * n; O.aeng = out.p + 3 * n;
-        O.astress = out.p + 4 * n; O.afd = out.p + 13 * n; O.scal = out.p + 22 * n; O.mxatms = mxatms;
+        O.astress = out.p + 4 * n; O.afd = out.p + 13 * n; O.scal = out.p + 22 * n; O.mxatms = mxatms; O.nwb = nwb; O.mxb = mxb;
         return O;
     }
 };
@@ -838,7 +868,12 @@ extern "C" {
 
 int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle)
 {
-    if (!handle || nttm2 < 3 || nttm2 % 3) return MBPOL_B200_EINVAL;
+    return mbpol_b200_init_batched(nttm2, 1, device, flags, handle);
+}
+
+int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_b200_handle** handle)
+{
+    if (!handle || nttm2 < 3 || nttm2 % 3 || nbeads < 1 || (long long)nbeads * nttm2 > 0x3fffffffLL) return MBPOL_B200_EINVAL;
     *handle = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MBPOL_B200_ENODEVICE;
@@ -849,7 +884,7 @@ int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle
     if (cudaSetDevice(device) != cudaSuccess) return MBPOL_B200_ECUDA;
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
-    h->device = device; h->nw = nttm2 / 3; h->flags = flags; h->engine = default_engine();
+    h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine();
     if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
         allow_smem(k_dimers<2>, SMEM2C) != cudaSuccess || allow_smem(k_trimers<2>, SMEM3C) != cudaSuccess) {
         delete h;
@@ -890,11 +925,14 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
                       const double* xxx, const double* yyy, const double* zzz, const double* vxx, const double* vyy, const double* vzz)
 {
     if (!h) return MBPOL_B200_EINVAL;
-    if (imcon < 1 || imcon > 3 || !cell || nttm2 != 3 * h->nw || !listttm2 || mxatms < nttm2 || !xxx || !yyy || !zzz) {
+    if (imcon < 1 || imcon > 3 || !cell || nttm2 != 3 * h->nwb || !listttm2 || mxatms < nttm2 || !xxx || !yyy || !zzz) {
         h->err = "mbpol_b200_upload: invalid argument (imcon must be 1, 2 or 3; nttm2 must match init)";
         return MBPOL_B200_EINVAL;
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
+    // bead-batched handles: the arrays hold nbeads consecutive systems of mxatms atoms (one bead otherwise)
+    h->mxb = mxatms;
+    mxatms *= h->nbeads;
     h->mxatms = mxatms; h->imcon = imcon;
     const size_t n = mxatms;
     CellInfo& C = h->C;
@@ -921,12 +959,23 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
         h->G.nc[k] = nc;
         h->ncells *= nc;
     }
+    h->G.nwb = h->nwb;
+    h->G.ncb = h->ncells;
+    h->ncells *= h->nbeads;
     CUDA_TRY(h, h->xyz.reserve(3 * n));
-    CUDA_TRY(h, h->list.reserve(nttm2));
+    CUDA_TRY(h, h->list.reserve((size_t)nttm2 * h->nbeads));
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p, xxx, n * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + n, yyy, n * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + 2 * n, zzz, n * 8, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->list.p, listttm2, (size_t)nttm2 * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->nbeads == 1) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->list.p, listttm2, (size_t)nttm2 * 4, cudaMemcpyHostToDevice, h->stream));
+    } else {   // the same topology in every bead: atom indices shifted by the bead's offset into the concatenated arrays
+        h->host_list.resize((size_t)nttm2 * h->nbeads);
+        for (int b = 0; b < h->nbeads; ++b)
+            for (int t = 0; t < nttm2; ++t) h->host_list[(size_t)b * nttm2 + t] = listttm2[t] + b * h->mxb;
+        CUDA_TRY(h, cudaMemcpyAsync(h->list.p, h->host_list.data(), h->host_list.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     h->have_vel = vxx && vyy && vzz;
     if (h->have_vel) {
         CUDA_TRY(h, h->vel.reserve(3 * n));
@@ -1039,8 +1088,7 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
     if (h->have_vel) {
-        const int nreal = 3 * nw;   // the O/H atoms; compute_heat_flux2 loops 1..3*mxatms/4 (heatcurrent.f90:710)
-        k_flux<<<(nreal + 255) / 256, 256, 0, s>>>(nreal, O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
+        k_flux<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[4], s));
@@ -1070,7 +1118,7 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
     CUDA_TRY(h, cudaMemcpyAsync(P, h->out.p, (atomic_energy ? 4 : 3) * n * 8, cudaMemcpyDeviceToHost, h->stream));
     if (atomic_stress) CUDA_TRY(h, cudaMemcpyAsync(P + 4 * n, h->out.p + 4 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
     if (atomic_fdecomp) CUDA_TRY(h, cudaMemcpyAsync(P + 13 * n, h->out.p + 13 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, NSCAL * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     // accumulate into the caller's arrays (the reference's "+=" semantics); a few host threads for the 22*mxatms adds
     struct Job { double* dst; const double* src; size_t len; };
@@ -1094,13 +1142,15 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         work(0);
         for (auto& t : th) t.join();
     }
-    const double* sc = P + 22 * n;
-    if (eng2) *eng2 += sc[S_ENG2];
-    if (vir2) *vir2 += sc[S_VIR2];
-    if (eng3) *eng3 += sc[S_ENG3];
-    if (vir3) *vir3 += sc[S_VIR3];
-    if (stress) for (int q = 0; q < 9; ++q) stress[q] += sc[S_STRESS + q];
-    if (jflux) for (int q = 0; q < 9; ++q) jflux[q] = sc[S_JFLUX + q];
+    for (int b = 0; b < h->nbeads; ++b) {     // scalars are per bead: eng2[b], ..., stress[9*b + q], jflux[9*b + q]
+        const double* sc = P + 22 * n + (size_t)b * NSCAL;
+        if (eng2) eng2[b] += sc[S_ENG2];
+        if (vir2) vir2[b] += sc[S_VIR2];
+        if (eng3) eng3[b] += sc[S_ENG3];
+        if (vir3) vir3[b] += sc[S_VIR3];
+        if (stress) for (int q = 0; q < 9; ++q) stress[9 * b + q] += sc[S_STRESS + q];
+        if (jflux) for (int q = 0; q < 9; ++q) jflux[9 * b + q] = sc[S_JFLUX + q];
+    }
     return MBPOL_B200_OK;
 }
 
@@ -1117,6 +1167,16 @@ int mbpol_b200_forces(mbpol_b200_handle* h, int imcon, const double* cell, int n
     if (int rc = mbpol_b200_upload(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, vxx, vyy, vzz)) return rc;
     if (int rc = mbpol_b200_compute(h)) return rc;
     return mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+}
+
+int mbpol_b200_forces_batched(mbpol_b200_handle* h, int nbeads, int imcon, const double* cell, int nttm2, const int* listttm2, int mxatms,
+                              const double* xxx, const double* yyy, const double* zzz, double* fxx, double* fyy, double* fzz, double* eng2,
+                              double* vir2, double* eng3, double* vir3, double* stress, double* atomic_energy, double* atomic_stress,
+                              double* atomic_fdecomp, const double* vxx, const double* vyy, const double* vzz, double* jflux)
+{
+    if (!h || nbeads != h->nbeads) return MBPOL_B200_EINVAL;
+    return mbpol_b200_forces(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress,
+                             atomic_energy, atomic_stress, atomic_fdecomp, vxx, vyy, vzz, jflux);
 }
 
 int mbpol_b200_device_outputs(mbpol_b200_handle* h, void** dev_ptr, long long* count)

@@ -49,6 +49,18 @@ int mbpol_b200_fini(mbpol_b200_handle* handle);
 const char* mbpol_b200_last_error(const mbpol_b200_handle* handle);
 void mbpol_b200_cutoffs(double* r2f, double* r3f);
 
+/* Bead-batched variant (PIMD/CMD, multibead.f90:25-93: every bead is an independent replica of the same topology with its
+ * own coordinates): ONE list build and ONE pair of evaluation launches for all beads.  Arrays are [nbeads][mxatms]
+ * (bead-major, each bead laid out like the single-system arrays); eng2/vir2/eng3/vir3 are [nbeads], stress and jflux
+ * [nbeads][9]; cell and listttm2 are shared by all beads.  mbpol_b200_init == mbpol_b200_init_batched(nbeads = 1). */
+int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_b200_handle** handle);
+int mbpol_b200_forces_batched(mbpol_b200_handle* handle, int nbeads, int imcon, const double* cell, int nttm2,
+                              const int* listttm2, int mxatms, const double* xxx, const double* yyy, const double* zzz,
+                              double* fxx, double* fyy, double* fzz,
+                              double* eng2, double* vir2, double* eng3, double* vir3, double* stress,
+                              double* atomic_energy, double* atomic_stress, double* atomic_fdecomp,
+                              const double* vxx, const double* vyy, const double* vzz, double* jflux);
+
 /* Work split exactly like `do t = bead_rank, n-1, bead_size` (mbpol.f90:218-226, 311-314) in spirit: with
  * (rank, nranks) != (0,1) the handle evaluates only its contiguous shard of the dimer and trimer lists and
  * the caller's existing gdsum over comm_bead (dlpoly_cmd.f:2551, 2568; heatcurrent.f90:1129-1259), or an NCCL
@@ -80,7 +92,7 @@ int mbpol_b200_forces(mbpol_b200_handle* handle, int imcon, const double* cell, 
  *   _download: device -> host copy and accumulation into the caller's arrays (same semantics as _forces)
  * mbpol_b200_device_outputs exposes the packed FP64 device buffer
  *   [ fxx | fyy | fzz | atomic_energy | atomic_stress(9) | atomic_fdecomp(9) ](each mxatms) [ scalars(32) ]
- *   scalars: 0 eng2, 1 vir2, 2 eng3, 3 vir3, 4..12 stress, 13..21 jflux, 22 n_dimers(shard), 23 n_trimers(shard)
+ *   scalars (32 per bead): 0 eng2, 1 vir2, 2 eng3, 3 vir3, 4..12 stress, 13..21 jflux, rest reserved
  * so that one ncclAllReduce(sum, double) over `count` elements finishes a multi-GPU step. */
 int mbpol_b200_upload(mbpol_b200_handle* handle, int imcon, const double* cell, int nttm2, const int* listttm2,
                       int mxatms, const double* xxx, const double* yyy, const double* zzz,

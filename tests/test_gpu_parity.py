@@ -211,3 +211,71 @@ def test_full_size_properties_4096(mb, oracle, synth):
         ref = oracle.trimer(w[q, :9], w[q, 9:18], w[q, 18:], ref=oracle.have_reference)
         sc = max(abs(ref[0]), np.abs(np.r_[ref[1], ref[2], ref[3]]).max())
         assert abs(E[q] - ref[0]) <= E_TOL * sc and np.abs(g[q] - np.r_[ref[1], ref[2], ref[3]]).max() <= F_TOL * sc
+
+
+def _sheared_box(synth, nw, imcon, seed=21):
+    """Non-cubic cells: the oxygens of a cubic box are mapped affinely into the new cell, the molecules stay rigid."""
+    box = dict(synth.make_water_box(nw, seed=seed))
+    L = box["L"]
+    if imcon == 2:
+        cell = np.diag([L, 1.12 * L, 0.93 * L])
+    else:
+        cell = np.array([[L, 0.0, 0.0], [0.21 * L, 1.05 * L, 0.0], [0.08 * L, -0.17 * L, 0.96 * L]])   # rows = cell vectors
+    n3 = 3 * nw
+    pos = np.stack([box["xxx"], box["yyy"], box["zzz"]], 1)
+    mol = pos[:n3].reshape(nw, 3, 3)
+    rel = mol - mol[:, :1]
+    rel -= L * np.round(rel / L)                       # un-split molecules of the cubic box
+    frac = mol[:, 0] / L                               # fractional oxygen coordinates in the cube
+    newO = frac @ cell
+    pos[:n3] = (newO[:, None, :] + rel).reshape(n3, 3)
+    box["imcon"] = imcon
+    box["cell"] = cell.ravel().copy()
+    for k, c in zip(("xxx", "yyy", "zzz"), range(3)):
+        box[k] = np.ascontiguousarray(pos[:, c])
+    return box
+
+
+@pytest.mark.parametrize("imcon", [2, 3])
+def test_non_cubic_cells_against_oracle(mb, oracle, synth, imcon):
+    """Orthorhombic (imcon 2) and triclinic (imcon 3, invert.f) cells: lists bit-exact, values within tolerance."""
+    box = _sheared_box(synth, 343, imcon)
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    out = mb.run_box(h, box, want_stress=True)
+    d, t = mb.mbpol_lists(h)
+    mb.mbpol_fini(h)
+    ref = oracle.forces(box, mode="listed", use_ref=oracle.have_reference, nthreads=os.cpu_count())
+    assert len(t) > 1000
+    assert np.array_equal(sort_rows(d), sort_rows(ref["dimers"]))
+    assert np.array_equal(sort_rows(t), sort_rows(ref["trimers"]))
+    compare(out, ref, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress"))
+
+
+def test_bead_batched_matches_single_systems(mb, synth):
+    """PIMD-style batch: 5 beads x 64 waters in ONE call == 5 independent calls."""
+    nb, nw = 5, 64
+    boxes = [synth.make_water_box(nw, seed=100 + b) for b in range(nb)]      # same L (same density), different coordinates
+    n = boxes[0]["mxatms"]
+    stack = lambda k: np.ascontiguousarray(np.stack([b[k] for b in boxes]))
+    X, Y, Z, VX, VY, VZ = (stack(k) for k in ("xxx", "yyy", "zzz", "vxx", "vyy", "vzz"))
+    F = [np.zeros((nb, n)) for _ in range(3)]
+    ae, ast, afd = np.zeros((nb, n)), np.zeros((nb, 9 * n)), np.zeros((nb, 9 * n))
+    h = mb.mbpol_init_batched(boxes[0]["nttm2"], nb, flags=7)
+    r = mb.mbpol_forces_batched(h, 1, boxes[0]["cell"], boxes[0]["nttm2"], boxes[0]["listttm2"], X, Y, Z, F[0], F[1], F[2],
+                                atomic_energy=ae, atomic_stress=ast, atomic_fdecomp=afd, vxx=VX, vyy=VY, vzz=VZ)
+    c = mb.mbpol_counts(h)
+    mb.mbpol_fini(h)
+    h1 = mb.mbpol_init(boxes[0]["nttm2"], flags=7)
+    ntri = 0
+    for b in range(nb):
+        one = mb.run_box(h1, boxes[b], want_stress=True)
+        ntri += mb.mbpol_counts(h1)["trimers"]
+        for k in ("eng2", "vir2", "eng3", "vir3"):
+            assert abs(r[k][b] - one[k]) <= 1e-11 * abs(one[k]), (b, k)
+        assert rel_rms(F[0][b], one["fxx"]) <= 1e-11 and rel_rms(F[2][b], one["fzz"]) <= 1e-11
+        assert rel_rms(ae[b], one["atomic_energy"]) <= 1e-11
+        assert rel_rms(ast[b], one["atomic_stress"]) <= 1e-11 and rel_rms(afd[b], one["atomic_fdecomp"]) <= 1e-11
+        assert rel_rms(r["stress"][b], one["stress"]) <= 1e-11
+        assert np.abs(r["jflux"][b] - one["jflux"]).max() <= 1e-10 * np.abs(one["jflux"]).max()
+    mb.mbpol_fini(h1)
+    assert c["trimers"] == ntri
