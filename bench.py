@@ -152,10 +152,47 @@ def run_reference(args, box, rank):
 
 def workload_config(box, args, nd, nt):
     return {"workload": "%d H2O MB-pol box (cubic, L=%.2f A, seed %d): 2B+3B energies, forces, per-atom energy and "
-                        "force-decomposition tensor, heat-flux contractions" % (box["nw"], box["L"], box["seed"]),
+                        "force-decomposition tensor%s, heat-flux contractions" % (box["nw"], box["L"], box["seed"], " and per-atom stress" if args.flags & 4 else ""),
             "n_waters": box["nw"], "n_dimers": int(nd), "n_trimers": int(nt), "flags": args.flags,
             "parallelism": "work-list shards x%d, replicated coordinates, one all-reduce" % args.gpus,
             "l2": "flushed between timed steps (256 MiB memset)"}
+
+
+def run_beads(args, mb, synth):
+    """BASELINE config 5: nbeads replicas of an nw-water box in ONE batched call (PIMD/CMD, multibead.f90:25-93)."""
+    import torch
+    nb = args.beads
+    boxes = [synth.make_water_box(args.nw, seed=1005 + b) for b in range(nb)]
+    n = boxes[0]["mxatms"]
+    stack = lambda k: np.ascontiguousarray(np.stack([b[k] for b in boxes]))
+    X, Y, Z, VX, VY, VZ = (stack(k) for k in ("xxx", "yyy", "zzz", "vxx", "vyy", "vzz"))
+    F = [np.zeros((nb, n)) for _ in range(3)]
+    ae = np.zeros((nb, n))
+    afd = np.zeros((nb, 9 * n)) if args.flags & 2 else None
+    h = mb.mbpol_init_batched(boxes[0]["nttm2"], nb, flags=args.flags)
+    call = lambda: mb.mbpol_forces_batched(h, 1, boxes[0]["cell"], boxes[0]["nttm2"], boxes[0]["listttm2"], X, Y, Z, F[0], F[1], F[2],
+                                           atomic_energy=ae, atomic_fdecomp=afd, vxx=VX, vyy=VY, vzz=VZ)
+    for _ in range(max(args.warmup, 3)):
+        call()
+    t, dev = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        call()
+        t.append(time.perf_counter() - t0)
+        dev.append(mb.mbpol_kernel_times(h))
+    c = mb.mbpol_counts(h)
+    ms_dev = float(np.mean([d["total_ms"] for d in dev]))
+    line = {"metric": METRIC, "value": c["trimers"] / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%d beads x %d H2O MB-pol, bead-batched 2B+3B in one call" % (nb, args.nw), "n_dimers": c["dimers"],
+                       "n_trimers": c["trimers"], "flags": args.flags},
+            "e2e": {"value": c["trimers"] / float(np.mean(t)), "unit": UNIT, "ms_per_step": 1e3 * float(np.mean(t)),
+                    "h2d_bytes_per_step": 8 * nb * n * 6, "d2h_bytes_per_step": 8 * nb * (n * (4 + (9 if afd is not None else 0)) + 32)},
+            "gpu_launches": int(dev[-1]["launches"]) * args.steps,
+            "phases_ms": {k: float(np.mean([q[k] for q in dev])) for k in ("lists_ms", "k2b_ms", "k3b_ms", "total_ms")}}
+    print(json.dumps(line))
+    mb.mbpol_fini(h)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -166,9 +203,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nw", type=int, default=32768, help="waters in the synthetic box (BASELINE configs: 4096, 32768)")
-    ap.add_argument("--flags", type=int, default=3, help="1 atomic energy | 2 force decomposition | 4 atomic stress (HEAT_STRESS)")
+    ap.add_argument("--flags", type=int, default=7,
+                    help="1 atomic energy | 2 force decomposition | 4 atomic stress (HEAT_STRESS); default all three: forces + per-atom energy, "
+                         "W and S (the north_star target); the reference default build corresponds to 3")
     ap.add_argument("--cpu-sample", type=int, default=0, help="trimers per CPU-baseline sample (default 4000 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default=None, help="read the box from a DL_POLY CONFIG file instead of the synthetic generator")
+    ap.add_argument("--beads", type=int, default=1, help="bead-batched evaluation (BASELINE config 5: --beads 32 --nw 512), 1 GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -178,7 +219,14 @@ def main():
 
     import mbpol_b200 as mb
     from mbpol_b200 import synth
-    box = synth.make_water_box(args.nw)
+    if args.config:
+        from mbpol_b200 import config_io
+        box = config_io.read_config(args.config)
+        args.nw = box["nw"]
+    else:
+        box = synth.make_water_box(args.nw)
+    if args.beads > 1:
+        return run_beads(args, mb, synth)
 
     if args.impl == "reference":
         run_reference(args, box, rank)
