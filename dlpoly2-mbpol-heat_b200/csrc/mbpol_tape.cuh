@@ -38,10 +38,14 @@ __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("s
         nv_ = xs_t + (vw_ >> 16) * TAPE_COL;                                                             \
         nxu = tape_lds(nu_); nxw = tape_lds(nw_); nxv = tape_lds(nv_);                                   \
         TAPE_LDS_V2(nq0x, nq0y, CP, 0);                                                                  \
+        TAPE_LDS_V2(nq1x, nq1y, CP, 16);                                                                 \
+        TAPE_LDS_V2(nq2x, nq2y, CP, 32);                                                                 \
+        TAPE_LDS_V2(nq3x, nq3y, CP, 48);                                                                 \
     }
 #define TAPE_ROW_PRE(ROWBYTES)                                                                           \
     const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
     const double xu = nxu, xw = nxw, xv = nxv, q0x = nq0x, q0y = nq0y;                                   \
+    const double q1x = nq1x, q1y = nq1y, q2x = nq2x, q2y = nq2y, q3x = nq3x, q3y = nq3y;                 \
     const double p2 = xv * xw, P = p2 * xu;                                                              \
     double S0 = q0x, S1 = 0.0, S2 = 0.0, S3 = 0.0;                                                       \
     TAPE_ROW_FETCH(min(row + 1, row_last), cp + (ROWBYTES))
@@ -72,8 +76,8 @@ extern __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
 
 template <int NV>
 struct TapeSmem {   // dynamic shared memory layout
-    double buf[2][TAPE_CHUNK_DOUBLES];   // staged tape chunks (16-byte aligned)
-    double xs[NV + 1][TAPE_BS];          // x, per-thread columns (dynamic-index reads); row NV = the unit variable
+    double buf[2][TAPE_CHUNK_DOUBLES];   // staged tape chunks (16-byte aligned); prefetches may run <= 64 B past a chunk,
+    double xs[NV + 1][TAPE_BS];          // i.e. into buf[1] / xs: harmless reads.  x, per-thread columns; row NV = unit variable
     double gs[NV + 1][TAPE_BS];          // gradient contributions with a dynamic index; row NV = dump slot
 };
 
@@ -126,7 +130,7 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
         const unsigned row_last = chunks[k + 1][1] - 1;    // last row of this chunk (prefetch clamp)
         const int sg1 = chunks[k + 1][0];
         unsigned nu_, nw_, nv_;
-        double nxu, nxw, nxv, nq0x, nq0y;
+        double nxu, nxw, nxv, nq0x, nq0y, nq1x, nq1y, nq2x, nq2y, nq3x, nq3y;   // TAPE_NPF = 4 prefetched pairs
         TAPE_ROW_FETCH(row, cp)
         for (int sg = chunks[k][0]; sg < sg1; ++sg) {
             const unsigned seg = segs[sg];
@@ -189,8 +193,11 @@ struct TapeCSmem {
 #define TAPE_ROW_PRE(ROWBYTES)                                                                           \
     const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
     const double xu = nxu, xw = nxw, xv = nxv;                                                           \
-    double q0x, q0y;                                                                                     \
+    double q0x, q0y, q1x, q1y, q2x, q2y, q3x, q3y;                                                       \
     TAPE_LD2(q0x, q0y, cp, 0);                                                                           \
+    TAPE_LD2(q1x, q1y, cp, 16);                                                                          \
+    TAPE_LD2(q2x, q2y, cp, 32);                                                                          \
+    TAPE_LD2(q3x, q3y, cp, 48);                                                                          \
     const double p2 = xv * xw, P = p2 * xu;                                                              \
     double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0; /* a tape value must never be an FMA ADDEND: ptxas then */ \
     TAPE_ROW_FETCH(min(row + 1, row_last))         /* drops the whole stream from LDCU to vector LDC       */

@@ -36,6 +36,7 @@ import gen_poly as G
 OUTD = G.OUTD
 CHUNK = 1024          # doubles per staged tape chunk (8 KB), shared-memory tape engine
 CWINDOW = G.CWINDOW    # doubles of the constant-bank window (42 KB), constant tape engine
+NPF = 4               # tape pairs of the NEXT row prefetched by every row (software pipelining across rows)
 NSUM = 2              # independent partial sums of the Horner accumulator S (shortens the dependent DFMA chain)
 
 
@@ -123,7 +124,7 @@ def emit_header(tag, nv, rows, types, mode):
     L = ["// generated by tools/gen_tape.py (%s, trie order=%s) -- do not edit" % (tag, mode), "#pragma once",
          "#define TAPE%s_NV %d" % (T, nv), "#define TAPE%s_NROWS %d" % (T, len(rows)), "#define TAPE%s_NTAPE %d" % (T, len(tape)),
          "#define TAPE%s_NSEGS %d" % (T, len(segs)), "#define TAPE%s_NCHUNKS %d" % (T, len(chunks) - 1),
-         "#define TAPE%s_NTYPES %d" % (T, nt), "#define TAPE%s_FP64_INSTR %d" % (T, nfma), "#define TAPE_CHUNK_DOUBLES %d" % CHUNK, "#define TAPE_NSUM %d" % NSUM]
+         "#define TAPE%s_NTYPES %d" % (T, nt), "#define TAPE%s_FP64_INSTR %d" % (T, nfma), "#define TAPE_CHUNK_DOUBLES %d" % CHUNK, "#define TAPE_NSUM %d" % NSUM, "#define TAPE_NPF %d" % NPF]
     L.append("static const unsigned TAPE%s_ROWVARS_HOST[%d] = {%s};" % (T, len(rowvars), ",".join(str(w) for w in rowvars)))
     L.append("static const unsigned TAPE%s_SEGS_HOST[%d] = {%s};" % (T, len(segs), ",".join(str(w) for w in segs)))
     L.append("static const short TAPE%s_COEFIDX_HOST[%d] = {%s};" % (T, len(tape), ",".join(str(c) for c in tape)))
@@ -141,7 +142,7 @@ def emit_header(tag, nv, rows, types, mode):
     L.append("#define TAPE%s_SEGMENT_SWITCH(type, nrows) { \\" % T)
     for t in range(min(nt, int(os.environ.get("TAPE_MAXTYPES", "1000")))):      # TAPE_MAXTYPES: compile-time experiments only
         vs = by_id[t]
-        body, have = [], {0}
+        body, have = [], set(range(NPF))          # pairs 0..NPF-1 were prefetched while the previous row was computed
         for i, v in enumerate(vs):
             slot = 1 + i
             pair, lane = slot // 2, slot % 2
