@@ -180,8 +180,9 @@ struct TapeCSmem {
 #undef TAPE_ROW_POST
 /* the tape pointer is a .const-space address kept opaque to the optimiser (inline PTX), so that ptxas sees a clean
    warp-uniform chain  mov -> add imm -> ld.const [reg+imm]  and emits LDCU with a uniform-register base */
-#define TAPE_LD2(vx, vy, ca, imm) asm volatile("ld.const.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "l"(ca), "n"(imm))
-#define TAPE_ADVANCE(ca, bytes) asm volatile("add.u64 %0, %0, %1;" : "+l"(ca) : "n"(bytes))
+/* not volatile: the window is read-only while a kernel runs, so the scheduler may hoist these loads across rows */
+#define TAPE_LD2(vx, vy, ca, imm) asm("ld.const.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "l"(ca), "n"(imm))
+#define TAPE_ADVANCE(ca, bytes) asm("add.u64 %0, %0, %1;" : "+l"(ca) : "n"(bytes))
 #define TAPE_ROW_FETCH(ROWIDX)                                                                           \
     {                                                                                                    \
         const unsigned vw_ = rowvars[ROWIDX];                                                            \
