@@ -29,8 +29,6 @@
 __constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];   // PTX-engine coefficient tables [2B | 3B] or one constant-tape window
 __constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
 __constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
-__constant__ int c_tape_cpass2b[TAPE2B_NCPASS + 1][3];
-__constant__ int c_tape_cpass3b[TAPE3B_NCPASS + 1][3];
 __constant__ MbpolParams mbpol_par;
 __constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
 __constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
@@ -765,8 +763,6 @@ int upload_constants(int device)
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(c_tape_csegs2b, TAPE2B_CSEGS_HOST, sizeof(TAPE2B_CSEGS_HOST)) != cudaSuccess) return 1;
     if (cudaMemcpyToSymbol(c_tape_csegs3b, TAPE3B_CSEGS_HOST, sizeof(TAPE3B_CSEGS_HOST)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(c_tape_cpass2b, TAPE2B_CPASS_HOST, sizeof(TAPE2B_CPASS_HOST)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(c_tape_cpass3b, TAPE3B_CPASS_HOST, sizeof(TAPE3B_CPASS_HOST)) != cudaSuccess) return 1;
     {   // PTX engine: both coefficient tables as one device image of the constant window
         std::vector<double> w(MBPOL_NCOEF2B + MBPOL_NCOEF3B);
         std::copy(MBPOL_COEF2B_HOST, MBPOL_COEF2B_HOST + MBPOL_NCOEF2B, w.begin());

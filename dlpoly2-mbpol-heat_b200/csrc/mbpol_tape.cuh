@@ -1,10 +1,12 @@
 // mbpol_tape.cuh -- the "coefficient tape" polynomial engine (see tools/gen_tape.py for the format and the why).
 //
-// One thread owns one cluster; all 256 threads of the CTA walk the SAME op list in lock step, so the op words are
-// warp-uniform (constant memory), the coefficient tape is staged global -> shared once per CTA with cp.async
-// (double buffered, 8 KB chunks) and read with broadcast LDS.128, and the only per-thread state is
-// x[NV], g[NV] (registers, static names) + a handful of trie-walk scalars.  Dynamic-index accesses to x / g
-// (once per op) go through per-thread columns in shared memory, addressed with 32-bit shared addresses.
+// The polynomial is a list of independent ROWS sorted by type (= leaf-variable set):
+//     P = x_u x_w x_v,  S = own + sum_c a_c x_c,  E += S P,  g_c += a_c P,  g_u += S x_w x_v,  g_w += S x_u x_v,  g_v += S x_u x_w.
+// One thread owns one cluster; all 256 threads of the CTA walk the SAME rows in lock step.  Engine 1 (this part of the
+// file): the coefficient tape is staged global -> shared once per CTA with cp.async (double buffered 8 KB chunks) and read
+// with broadcast LDS.128; one small counted loop per (chunk, type) segment, static register names for x[], g[]; the
+// (u,w,v) word of a row comes from constant memory; dynamic-index reads of x and updates of g go through per-thread
+// columns in shared memory (32-bit shared addresses).  Engine 2 (second half): the tape is read from the constant bank.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -49,13 +51,9 @@ __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("s
     const double p2 = xv * xw, P = p2 * xu;                                                              \
     double S0 = q0x, S1 = 0.0, S2 = 0.0, S3 = 0.0;                                                       \
     TAPE_ROW_FETCH(min(row + 1, row_last), cp + (ROWBYTES))
-#ifdef TAPE_EXPERIMENT_SKIP_WV   /* timing experiment only: WRONG gradients */
-#define TAPE_WV_UPDATES e = fma(S0, xu * xv + xu * xw, e);
-#else
 #define TAPE_WV_UPDATES                                                                                  \
     tape_sts(aw_ + gs_delta, fma(S0, xu * xv, tape_lds(aw_ + gs_delta)));                                \
     tape_sts(av_ + gs_delta, fma(S0, xu * xw, tape_lds(av_ + gs_delta)));
-#endif
 #define TAPE_ROW_POST(ROWBYTES)                                                                          \
     S0 = (S0 + S1) + (S2 + S3);                                                                          \
     e = fma(S0, P, e);                                                                                   \
@@ -159,8 +157,6 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
 extern __constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];
 extern __constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
 extern __constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
-extern __constant__ int c_tape_cpass2b[TAPE2B_NCPASS + 1][3];
-extern __constant__ int c_tape_cpass3b[TAPE3B_NCPASS + 1][3];
 
 // Head of every constant window (16 bytes = two tape slots): the bounds of the pass.  Read from FIXED constant-bank
 // addresses so that ptxas can prove the loop trip counts warp-uniform (a function argument or a table lookup is not enough:
