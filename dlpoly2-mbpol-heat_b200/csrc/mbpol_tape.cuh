@@ -3,7 +3,7 @@
 // The polynomial is a list of independent ROWS sorted by type (= leaf-variable set):
 //     P = x_u x_w x_v,  S = own + sum_c a_c x_c,  E += S P,  g_c += a_c P,  g_u += S x_w x_v,  g_w += S x_u x_v,  g_v += S x_u x_w.
 // One thread owns one cluster; all 256 threads of the CTA walk the SAME rows in lock step.  Engine 1 (this part of the
-// file): the coefficient tape is staged global -> shared once per CTA with cp.async (double buffered 8 KB chunks) and read
+// file): the coefficient tape is staged global -> shared once per CTA with cp.async (double buffered 16 KB chunks) and read
 // with broadcast LDS.128; one small counted loop per (chunk, type) segment, static register names for x[], g[]; the
 // (u,w,v) word of a row comes from constant memory; dynamic-index reads of x and updates of g go through per-thread
 // columns in shared memory (32-bit shared addresses).  Engine 2 (second half): the tape is read from the constant bank.
