@@ -53,3 +53,35 @@ def test_generated_schedule_matches_tables(tmp_path, oracle):
             Er, gr = oracle.poly(tag, a, x)
             assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
             assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()
+
+
+def test_tape_rows_reproduce_the_polynomials(oracle):
+    """tools/gen_tape.py: the flattened rows (E += S*P, S = own + sum a_c x_c, P = x_u x_w x_v) of the tape engines are
+    the same polynomial and gradient as the monomial tables -- checked in numpy from the generator's own row list."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_poly
+    import gen_tape
+    d = np.load(gen_poly.DATA)
+    rng = np.random.default_rng(11)
+    for tag, nv, mode in (("2b", 31, "identity"), ("3b", 36, "reverse")):
+        rows, types = gen_tape.build(tag, d["mono" + tag], nv, mode)
+        by_id = {t: vs for vs, t in types.items()}
+        a = oracle.coef(tag)
+        x = rng.uniform(0.1, 1.2, size=nv)
+        xe = np.concatenate([x, [1.0]])                 # pseudo-variable UNIT = nv
+        E, g = 0.0, np.zeros(nv + 1)
+        for (t, u, w, v, own, cs) in rows:
+            vs = by_id[t]
+            assert len(vs) == len(cs)
+            P = xe[u] * xe[w] * xe[v]
+            S = (a[own] if own >= 0 else 0.0) + sum(a[k] * x[c] for k, c in zip(cs, vs))
+            E += S * P
+            for k, c in zip(cs, vs):
+                g[c] += a[k] * P
+            g[u] += S * xe[w] * xe[v]
+            g[w] += S * xe[u] * xe[v]
+            g[v] += S * xe[u] * xe[w]
+        Er, gr = oracle.poly(tag, a, x)
+        assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+        assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()
+        assert len(types) <= 64 and max(len(v) for v in by_id.values()) <= nv
