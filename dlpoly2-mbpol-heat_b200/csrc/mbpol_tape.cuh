@@ -30,40 +30,60 @@ __device__ __forceinline__ void tape_sts(unsigned a, double v) { asm volatile("s
 #define TAPE_PRAGMA_(x) _Pragma(#x)
 #define TAPE_PRAGMA(x) TAPE_PRAGMA_(x)
 #define TAPE_ROW_LOOP(nrows) TAPE_PRAGMA(unroll TAPE_UNROLL) for (unsigned r_ = 0; r_ < (nrows); ++r_)
-// The row header -- (u,w,v) word, the three x loads and the first tape pair -- is software pipelined: the header of
-// the NEXT row (nu_/nw_/nv_, nxu/nxw/nxv, nq0x/nq0y; loaded by TAPE_ROW_FETCH) is issued before the FMAs of this row.
+// Segment = run of rows with the same (type, u): x_u is a register for the whole segment, sum_rows S x_w x_v is
+// collected in Gu (E += x_u Gu and g_u += Gu once per segment).  Only w and v are dynamic per row: two x reads and two
+// gradient read-modify-writes in the per-thread shared-memory columns.
+#define TAPE_SEG_BEGIN(seg)                                                                              \
+    const unsigned type = (seg) & 255u, nrows = (seg) >> 16;                                             \
+    const unsigned au_ = xs_t + (((seg) >> 8) & 255u) * TAPE_COL;                                        \
+    const double xu = tape_lds(au_);                                                                     \
+    double Gu = 0.0;
+#define TAPE_SEG_END                                                                                     \
+    e = fma(Gu, xu, e);                                                                                  \
+    tape_sts(au_ + gs_delta, tape_lds(au_ + gs_delta) + Gu);
+// The row header -- (w,v) word, the two x loads and the first TAPE_NPF tape pairs -- is software pipelined: the header
+// of the NEXT row (nw_/nv_, nxw/nxv, nq*; loaded by TAPE_ROW_FETCH) is issued before the FMAs of this row.
+#define TAPE_ROW_HEADER(ROWIDX)                                                                          \
+        const unsigned vw_ = rowvars[ROWIDX];                                                            \
+        nw_ = xs_t + (vw_ & 255u) * TAPE_COL;                                                            \
+        nv_ = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL;                                                     \
+        nxv = tape_lds(nv_);                                                                             \
+        nxw = tape_lds(nw_);
 #define TAPE_ROW_FETCH(ROWIDX, CP)                                                                       \
     {                                                                                                    \
-        const unsigned vw_ = rowvars[ROWIDX];                                                            \
-        nu_ = xs_t + (vw_ & 255u) * TAPE_COL;                                                            \
-        nw_ = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL;                                                     \
-        nv_ = xs_t + (vw_ >> 16) * TAPE_COL;                                                             \
-        nxu = tape_lds(nu_); nxw = tape_lds(nw_); nxv = tape_lds(nv_);                                   \
-        TAPE_LDS_V2(nq0x, nq0y, CP, 0);                                                                  \
-        TAPE_LDS_V2(nq1x, nq1y, CP, 16);                                                                 \
-        TAPE_LDS_V2(nq2x, nq2y, CP, 32);                                                                 \
-        TAPE_LDS_V2(nq3x, nq3y, CP, 48);                                                                 \
+        TAPE_ROW_HEADER(ROWIDX)                                                                          \
+        TAPE_PF_LOADS(CP)                                                                                \
     }
-#define TAPE_ROW_PRE(ROWBYTES)                                                                           \
-    const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
-    const double xu = nxu, xw = nxw, xv = nxv, q0x = nq0x, q0y = nq0y;                                   \
-    const double q1x = nq1x, q1y = nq1y, q2x = nq2x, q2y = nq2y, q3x = nq3x, q3y = nq3y;                 \
-    const double p2 = xv * xw, P = p2 * xu;                                                              \
-    double S0 = q0x, S1 = 0.0, S2 = 0.0, S3 = 0.0;                                                       \
-    TAPE_ROW_FETCH(min(row + 1, row_last), cp + (ROWBYTES))
-#define TAPE_WV_UPDATES                                                                                  \
-    tape_sts(aw_ + gs_delta, fma(S0, xu * xv, tape_lds(aw_ + gs_delta)));                                \
-    tape_sts(av_ + gs_delta, fma(S0, xu * xw, tape_lds(av_ + gs_delta)));
-#define TAPE_ROW_POST(ROWBYTES)                                                                          \
-    S0 = (S0 + S1) + (S2 + S3);                                                                          \
-    e = fma(S0, P, e);                                                                                   \
-    tape_sts(au_ + gs_delta, fma(S0, p2, tape_lds(au_ + gs_delta)));                                     \
-    TAPE_WV_UPDATES                                                                                      \
-    cp += (ROWBYTES);                                                                                    \
-    ++row;
+// rows are evaluated in pairs (suffix S = a, b; K = 0, 1 = position in the pair): see tools/gen_tape.py
+#define TAPE_PAIR_LOOP(nrows) for (; r_ + 2 <= (nrows); r_ += 2)
+#define TAPE_ROW_PRE(ROWBYTES, S, K)                                                                     \
+    const unsigned aw_##S = nw_, av_##S = nv_;                                                           \
+    const double xw##S = nxw, xv##S = nxv;                                                               \
+    TAPE_PF_TAKE(S)                                                                                      \
+    const double p2##S = xv##S * xw##S, P##S = p2##S * xu;                                               \
+    double S0##S = q0x##S, S1##S = 0.0, S2##S = 0.0, S3##S = 0.0;                                        \
+    TAPE_ROW_FETCH(min(row + (K) + 1, row_last), cp + ((K) + 1) * (ROWBYTES))
+#define TAPE_ROW_TAIL(S)                                                                                 \
+    Gu = fma(S0##S, p2##S, Gu);                                                                          \
+    {                                                                                                    \
+        const double R_ = S0##S * xu;                                                                    \
+        tape_sts(av_##S + gs_delta, fma(R_, xw##S, tape_lds(av_##S + gs_delta)));                        \
+        tape_sts(aw_##S + gs_delta, fma(R_, xv##S, tape_lds(aw_##S + gs_delta)));                        \
+    }
+#define TAPE_ROW_POST(S)                                                                                 \
+    S0##S = TAPE_SSUM(S);                                                                                \
+    TAPE_ROW_TAIL(S)
+#define TAPE_ROWS_ADVANCE(BYTES, N)                                                                      \
+    cp += (BYTES);                                                                                       \
+    row += (N);
 
 #include "gen/tape_2b.h"
 #include "gen/tape_3b.h"
+#if TAPE_NSUM == 2      /* sum of the partial Horner accumulators in use (x + 0.0 is not folded away in FP64) */
+#define TAPE_SSUM(S) S0##S + S1##S
+#else
+#define TAPE_SSUM(S) (S0##S + S1##S) + (S2##S + S3##S)
+#endif
 
 extern __constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
 extern __constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
@@ -127,17 +147,18 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
         unsigned row = chunks[k][1];
         const unsigned row_last = chunks[k + 1][1] - 1;    // last row of this chunk (prefetch clamp)
         const int sg1 = chunks[k + 1][0];
-        unsigned nu_, nw_, nv_;
-        double nxu, nxw, nxv, nq0x, nq0y, nq1x, nq1y, nq2x, nq2y, nq3x, nq3y;   // TAPE_NPF = 4 prefetched pairs
+        unsigned nw_, nv_;
+        double nxw, nxv;
+        TAPE_PF_DECL                                       // the TAPE_NPF prefetched tape pairs of the next row
         TAPE_ROW_FETCH(row, cp)
         for (int sg = chunks[k][0]; sg < sg1; ++sg) {
-            const unsigned seg = segs[sg];
-            const unsigned type = seg & 255u, nrows = seg >> 8;
+            TAPE_SEG_BEGIN(segs[sg])
             if (WHICH == 3) {
                 TAPE3B_SEGMENT_SWITCH(type, nrows)
             } else {
                 TAPE2B_SEGMENT_SWITCH(type, nrows)
             }
+            TAPE_SEG_END
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }
@@ -174,6 +195,7 @@ struct TapeCSmem {
 #undef TAPE_ROW_FETCH
 #undef TAPE_ROW_PRE
 #undef TAPE_ROW_POST
+#undef TAPE_ROWS_ADVANCE
 /* the tape pointer is a .const-space address kept opaque to the optimiser (inline PTX), so that ptxas sees a clean
    warp-uniform chain  mov -> add imm -> ld.const [reg+imm]  and emits LDCU with a uniform-register base */
 /* not volatile: the window is read-only while a kernel runs, so the scheduler may hoist these loads across rows */
@@ -181,30 +203,21 @@ struct TapeCSmem {
 #define TAPE_ADVANCE(ca, bytes) asm("add.u64 %0, %0, %1;" : "+l"(ca) : "n"(bytes))
 #define TAPE_ROW_FETCH(ROWIDX)                                                                           \
     {                                                                                                    \
-        const unsigned vw_ = rowvars[ROWIDX];                                                            \
-        nu_ = xs_t + (vw_ & 255u) * TAPE_COL;                                                            \
-        nw_ = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL;                                                     \
-        nv_ = xs_t + (vw_ >> 16) * TAPE_COL;                                                             \
-        nxu = tape_lds(nu_); nxw = tape_lds(nw_); nxv = tape_lds(nv_);                                   \
+        TAPE_ROW_HEADER(ROWIDX)                                                                          \
     }
-#define TAPE_ROW_PRE(ROWBYTES)                                                                           \
-    const unsigned au_ = nu_, aw_ = nw_, av_ = nv_;                                                      \
-    const double xu = nxu, xw = nxw, xv = nxv;                                                           \
-    double q0x, q0y, q1x, q1y, q2x, q2y, q3x, q3y;                                                       \
-    TAPE_LD2(q0x, q0y, cp, 0);                                                                           \
-    TAPE_LD2(q1x, q1y, cp, 16);                                                                          \
-    TAPE_LD2(q2x, q2y, cp, 32);                                                                          \
-    TAPE_LD2(q3x, q3y, cp, 48);                                                                          \
-    const double p2 = xv * xw, P = p2 * xu;                                                              \
-    double S0 = 0.0, S1 = 0.0, S2 = 0.0, S3 = 0.0; /* a tape value must never be an FMA ADDEND: ptxas then */ \
-    TAPE_ROW_FETCH(min(row + 1, row_last))         /* drops the whole stream from LDCU to vector LDC       */
-#define TAPE_ROW_POST(ROWBYTES)                                                                          \
-    S0 = ((S0 + S1) + (S2 + S3)) + q0x;                                                                  \
-    e = fma(S0, P, e);                                                                                   \
-    tape_sts(au_ + gs_delta, fma(S0, p2, tape_lds(au_ + gs_delta)));                                     \
-    TAPE_WV_UPDATES                                                                                      \
-    TAPE_ADVANCE(cp, ROWBYTES);                                                                          \
-    ++row;
+#define TAPE_ROW_PRE(ROWBYTES, S, K)                                                                     \
+    const unsigned aw_##S = nw_, av_##S = nv_;                                                           \
+    const double xw##S = nxw, xv##S = nxv;                                                               \
+    TAPE_PF_CLOADS(S, (K) * (ROWBYTES))                                                                  \
+    const double p2##S = xv##S * xw##S, P##S = p2##S * xu;                                               \
+    double S0##S = 0.0, S1##S = 0.0, S2##S = 0.0, S3##S = 0.0; /* a tape value must never be an FMA ADDEND: */ \
+    TAPE_ROW_FETCH(min(row + (K) + 1, row_last))   /* ptxas then drops the whole stream from LDCU to vector LDC */
+#define TAPE_ROW_POST(S)                                                                                 \
+    S0##S = (TAPE_SSUM(S)) + q0x##S;                                                                     \
+    TAPE_ROW_TAIL(S)
+#define TAPE_ROWS_ADVANCE(BYTES, N)                                                                      \
+    TAPE_ADVANCE(cp, BYTES);                                                                             \
+    row += (N);
 
 // One pass: adds the rows [row0, row_last] = segments [sg0, sg1) of one constant window to (E, g).  x must already be in
 // registers; g/E are accumulated into.  The bounds MUST arrive as kernel parameters: when they are looked up from a
@@ -230,17 +243,17 @@ __device__ __forceinline__ void tape_eval_const_pass(int sg0, int sg1, unsigned 
     // .const address of the current row; the first two slots of the window hold the pass bounds (see TapeCPassHeader)
     unsigned long long cp = (unsigned long long)__cvta_generic_to_constant(mbpol_cwin) + 16;
     unsigned row = row0;
-    unsigned nu_, nw_, nv_;
-    double nxu, nxw, nxv;
+    unsigned nw_, nv_;
+    double nxw, nxv;
     TAPE_ROW_FETCH(row)
     for (int sg = sg0; sg < sg1; ++sg) {
-        const unsigned seg = segs[sg];
-        const unsigned type = seg & 255u, nrows = seg >> 8;
+        TAPE_SEG_BEGIN(segs[sg])
         if (WHICH == 3) {
             TAPE3B_SEGMENT_SWITCH(type, nrows)
         } else {
             TAPE2B_SEGMENT_SWITCH(type, nrows)
         }
+        TAPE_SEG_END
     }
 #pragma unroll
     for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);

@@ -37,6 +37,7 @@ OUTD = G.OUTD
 CHUNK = 2048          # doubles per staged tape chunk (16 KB), shared-memory tape engine (1024: +2 %, 4096: +7 % time)
 CWINDOW = G.CWINDOW    # doubles of the constant-bank window (42 KB), constant tape engine
 NPF = 4               # tape pairs of the NEXT row prefetched by every row (software pipelining across rows)
+PAIR = False          # see emit_header
 NSUM = 2              # independent partial sums of the Horner accumulator S (shortens the dependent DFMA chain)
 
 
@@ -74,7 +75,9 @@ def build(tag, mono, nv, mode):
             t = types.setdefault((), len(types))
             rows.append((t, UNIT, UNIT, c.var, c.coef, []))
     visit(root, [])
-    rows.sort(key=lambda r: (r[0], r[3], r[2], r[1]))
+    # (type, u) first: u, the variable next to the leaves, is almost a function of the type (72 (type,u) runs for the
+    # 3B polynomial, 51 for 2B), so it becomes a per-SEGMENT constant; inside a segment rows with the same w are adjacent
+    rows.sort(key=lambda r: (r[0], r[1], r[2], r[3]))
     nmono = sum(len(r[5]) + (1 if r[4] >= 0 else 0) for r in rows)
     assert nmono == len(monos), (nmono, len(monos))
     return rows, types
@@ -89,19 +92,18 @@ def emit_header(tag, nv, rows, types, mode):
     T = tag.upper()
     by_id = {t: vs for vs, t in types.items()}
     nt = len(types)
-    tape, rowvars = [], []
+    tape = []
     nfma = 0
     for (t, u, w, v, own, cs) in rows:
-        rowvars.append(u | (w << 8) | (v << 16))
         tape.append(own)
         tape.extend(cs)
         if len(tape) % 2:
             tape.append(-1)
-        nfma += 2 * len(cs) + 9
+        nfma += 2 * len(cs) + 7
 
     def partition(limit):
-        """Cut the (type-sorted) row list into pieces of <= limit tape slots; inside a piece, runs of equal type
-        are segments (type | nrows << 8).  Returns (segs, pieces) with pieces = (first seg, first row, first slot)."""
+        """Cut the sorted row list into pieces of <= limit tape slots; inside a piece, runs of equal (type, u) are
+        segments (type | u << 8 | nrows << 16).  Returns (segs, pieces) with pieces = (first seg, first row, first slot)."""
         segs, pieces = [], []
         used, pos, cur = limit + 1, 0, None
         for i, (t, u, w, v, own, cs) in enumerate(rows):
@@ -109,10 +111,10 @@ def emit_header(tag, nv, rows, types, mode):
             if used + n > limit:
                 pieces.append((len(segs), i, pos))
                 used, cur = 0, None
-            if cur != t:
-                segs.append(t)
-                cur = t
-            segs[-1] += 1 << 8
+            if cur != (t, u):
+                segs.append(t | (u << 8))
+                cur = (t, u)
+            segs[-1] += 1 << 16
             used += n
             pos += n
         assert pos == len(tape)
@@ -121,6 +123,8 @@ def emit_header(tag, nv, rows, types, mode):
 
     segs, chunks = partition(CHUNK)
     csegs, cpass = partition(CWINDOW - 2)      # two slots of every window hold the pass header
+    rowvars = [w | (v << 8) for (t, u, w, v, own, cs) in rows]      # row word: the two per-row dynamic variables
+    nfma += 2 * len(segs)
     L = ["// generated by tools/gen_tape.py (%s, trie order=%s) -- do not edit" % (tag, mode), "#pragma once",
          "#define TAPE%s_NV %d" % (T, nv), "#define TAPE%s_NROWS %d" % (T, len(rows)), "#define TAPE%s_NTAPE %d" % (T, len(tape)),
          "#define TAPE%s_NSEGS %d" % (T, len(segs)), "#define TAPE%s_NCHUNKS %d" % (T, len(chunks) - 1),
@@ -135,25 +139,44 @@ def emit_header(tag, nv, rows, types, mode):
     L.append("#define TAPE_CWINDOW_DOUBLES %d" % CWINDOW)
     L.append("static const unsigned TAPE%s_CSEGS_HOST[%d] = {%s};" % (T, len(csegs), ",".join(str(w) for w in csegs)))
     L.append("static const int TAPE%s_CPASS_HOST[%d][3] = {%s};" % (T, len(cpass), ",".join("{%d,%d,%d}" % c for c in cpass)))
-    L.append("// One counted loop per row type: TAPE_ROW_PRE loads (x_u, x_w, x_v), forms P and the first tape pair (q0x = own,")
+    L.append("// One counted loop per row type: TAPE_ROW_PRE takes (x_w, x_v) of the row, forms P and the first tape pair (q0x = own,")
     L.append("// q0y = first coefficient); the body accumulates S0/S1 (two partial Horner sums) and g[c] += a_c*P with static")
-    L.append("// register names; TAPE_ROW_POST(bytes) adds S*P to E, updates the three dynamic gradient slots and advances the tape.")
-    # an if-chain, not a switch: an indirect branch (BRX) makes ptxas give up on warp-uniformity of the tape pointer
-    L.append("#define TAPE%s_SEGMENT_SWITCH(type, nrows) { \\" % T)
-    for t in range(min(nt, int(os.environ.get("TAPE_MAXTYPES", "1000")))):      # TAPE_MAXTYPES: compile-time experiments only
-        vs = by_id[t]
+    L.append("// register names; TAPE_ROW_POST(bytes) adds S*x_w*x_v to the segment sum, updates g_v / the w-run sum and advances the tape.")
+    # the NPF prefetched pairs: declaration list, loads (shared-memory engine), hand-over to the row, direct loads (constant engine)
+    pf = ["nq%d%s" % (k, c) for k in range(NPF) for c in "xy"]
+    L.append("#define TAPE_PF_DECL double %s;" % ", ".join(pf))
+    L.append("#define TAPE_PF_LOADS(CP) %s" % " ".join("TAPE_LDS_V2(nq%dx, nq%dy, CP, %d);" % (k, k, 16 * k) for k in range(NPF)))
+    L.append("#define TAPE_PF_TAKE(S) const double %s;" % ", ".join("q%d%s##S = nq%d%s" % (k, c, k, c) for k in range(NPF) for c in "xy"))
+    L.append("#define TAPE_PF_CLOADS(S, OFF) double %s; %s" % (", ".join("q%d%s##S" % (k, c) for k in range(NPF) for c in "xy"),
+             " ".join("TAPE_LD2(q%dx##S, q%dy##S, cp, (OFF) + %d);" % (k, k, 16 * k) for k in range(NPF))))
+    # an if-chain, not a switch: an indirect branch (BRX) makes ptxas give up on warp-uniformity of the tape pointer.
+    # --pair (experiment, slower: 35.3 vs 31.5 ms): rows evaluated in explicit PAIRS (a, b) with all loads of both rows
+    # ahead of the gradient stores of either; the default leaves the interleaving to `#pragma unroll 2`.
+    def row_body(vs, sfx, k, nbytes):
         body, have = [], set(range(NPF))          # pairs 0..NPF-1 were prefetched while the previous row was computed
         for i, v in enumerate(vs):
             slot = 1 + i
             pair, lane = slot // 2, slot % 2
             if pair not in have:
                 have.add(pair)
-                body.append("double q%dx, q%dy; TAPE_LD2(q%dx, q%dy, cp, %d);" % (pair, pair, pair, pair, 16 * pair))
-            a = "q%d%s" % (pair, "xy"[lane])
-            acc = "S%d" % (i % NSUM)
-            body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, P, g[%d]);" % (acc, a, v, acc, v, a, v))
-        L.append("%sif ((type) == %d) { TAPE_ROW_LOOP(nrows) { TAPE_ROW_PRE(%d) %s TAPE_ROW_POST(%d) } } \\" % (
-            "else " if t else "", t, 8 * row_slots(len(vs)), " ".join(body), 8 * row_slots(len(vs))))
+                body.append("double q%dx%s, q%dy%s; TAPE_LD2(q%dx%s, q%dy%s, cp, %d);" % (pair, sfx, pair, sfx, pair, sfx, pair, sfx, k * nbytes + 16 * pair))
+            a = "q%d%s%s" % (pair, "xy"[lane], sfx)
+            acc = "S%d%s" % (i % NSUM, sfx)
+            body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, P%s, g[%d]);" % (acc, a, v, acc, v, a, sfx, v))
+        return " ".join(body)
+
+    L.append("#define TAPE%s_SEGMENT_SWITCH(type, nrows) { \\" % T)
+    for t in range(min(nt, int(os.environ.get("TAPE_MAXTYPES", "1000")))):      # TAPE_MAXTYPES: compile-time experiments only
+        vs = by_id[t]
+        nb = 8 * row_slots(len(vs))
+        if PAIR:
+            L.append("%sif ((type) == %d) { unsigned r_ = 0; \\" % ("else " if t else "", t))
+            L.append("  TAPE_PAIR_LOOP(nrows) { TAPE_ROW_PRE(%d, a, 0) %s TAPE_ROW_PRE(%d, b, 1) %s TAPE_ROW_POST(a) TAPE_ROW_POST(b) TAPE_ROWS_ADVANCE(%d, 2) } \\" % (
+                nb, row_body(vs, "a", 0, nb), nb, row_body(vs, "b", 1, nb), 2 * nb))
+            L.append("  if (r_ < (nrows)) { TAPE_ROW_PRE(%d, a, 0) %s TAPE_ROW_POST(a) TAPE_ROWS_ADVANCE(%d, 1) } } \\" % (nb, row_body(vs, "a", 0, nb), nb))
+        else:
+            L.append("%sif ((type) == %d) { TAPE_ROW_LOOP(nrows) { TAPE_ROW_PRE(%d, a, 0) %s TAPE_ROW_POST(a) TAPE_ROWS_ADVANCE(%d, 1) } } \\" % (
+                "else " if t else "", t, nb, row_body(vs, "a", 0, nb), nb))
     L.append("}")
     return "\n".join(L) + "\n", nfma, len(chunks) - 1, len(segs)
 
@@ -164,8 +187,12 @@ def main():
     ap.add_argument("--order2b", default="identity")
     ap.add_argument("--order3b", default="reverse")
     ap.add_argument("--nsum", type=int, default=NSUM)
+    ap.add_argument("--npf", type=int, default=NPF)
+    ap.add_argument("--pair", action="store_true")
     args = ap.parse_args()
     globals()["NSUM"] = args.nsum
+    globals()["NPF"] = args.npf
+    globals()["PAIR"] = args.pair
     d = np.load(G.DATA)
     os.makedirs(args.outdir, exist_ok=True)
     for tag, nv, mode in (("2b", 31, args.order2b), ("3b", 36, args.order3b)):
