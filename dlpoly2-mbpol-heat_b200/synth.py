@@ -80,3 +80,31 @@ def make_water_box(nw, seed=None, min_contact=1.5, max_sweeps=20):
         "xxx": np.ascontiguousarray(pos[:, 0]), "yyy": np.ascontiguousarray(pos[:, 1]), "zzz": np.ascontiguousarray(pos[:, 2]),
         "vxx": np.ascontiguousarray(vel[:, 0]), "vyy": np.ascontiguousarray(vel[:, 1]), "vzz": np.ascontiguousarray(vel[:, 2]),
     }
+
+
+def make_ion_box(nw_total=4096, nions=64, ions=("na", "cl"), seed=1004, min_contact=2.0):
+    """BASELINE config 4: the water box of make_water_box(nw_total) in which `nions` randomly chosen
+    waters are replaced by ions (alternating species, placed at the removed oxygen).  Ions are the FIRST atoms, as
+    mbnrg.f90:226-233 requires; then O,H,H per water; then the M-sites.  Waters closer than `min_contact` to an ion are
+    not removed (the synthetic lattice spacing of 3.1 A keeps ion-oxygen distances physical)."""
+    from .mbnrg import ION_CODES
+    base = make_water_box(nw_total, seed=seed)
+    rng = np.random.default_rng(seed + 17)
+    gone = np.sort(rng.choice(nw_total, size=nions, replace=False))
+    keep = np.setdiff1d(np.arange(nw_total), gone)
+    nw = len(keep)
+    pos_w = np.stack([base["xxx"], base["yyy"], base["zzz"]], 1)[:3 * nw_total].reshape(nw_total, 3, 3)
+    vel_w = np.stack([base["vxx"], base["vyy"], base["vzz"]], 1)[:3 * nw_total].reshape(nw_total, 3, 3)
+    mx = nions + 4 * nw
+    pos, vel = np.zeros((mx, 3)), np.zeros((mx, 3))
+    pos[:nions] = pos_w[gone, 0]
+    pos[nions:nions + 3 * nw] = pos_w[keep].reshape(-1, 3)
+    vel[nions:nions + 3 * nw] = vel_w[keep].reshape(-1, 3)
+    code = np.array([ION_CODES[ions[j % len(ions)]] for j in range(nions)], dtype=np.int32)
+    return {
+        "nw": nw, "nions": nions, "mxatms": mx, "nttm2": 3 * nw, "imcon": 1, "cell": base["cell"], "L": base["L"], "seed": seed,
+        "listttm2": np.arange(nions + 1, nions + 3 * nw + 1, dtype=np.int32), "listions": np.arange(1, nions + 1, dtype=np.int32),
+        "ion_code": code,
+        "xxx": np.ascontiguousarray(pos[:, 0]), "yyy": np.ascontiguousarray(pos[:, 1]), "zzz": np.ascontiguousarray(pos[:, 2]),
+        "vxx": np.ascontiguousarray(vel[:, 0]), "vyy": np.ascontiguousarray(vel[:, 1]), "vzz": np.ascontiguousarray(vel[:, 2]),
+    }

@@ -688,6 +688,7 @@ void oracle_ref_3b(const double* w1, const double* w2, const double* w3, double*
 }
 
 int oracle_image_vectors(int imcon, const double* cell, int n, double* dx) { return image_vectors(imcon, cell, n, dx); }
+void oracle_image_monomers(int imcon, const double* cell, int nw, double* xyz) { image_monomers(imcon, cell, nw, xyz); }
 
 // ------------------------------------------------------------------------------------------------
 // The driver: restatement of mbpol::mbpol_forces (mbpol.f90:98-449).

@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmbpol_oracle.so")
 REF_O2 = os.path.join(HERE, "_ref", "libmbpol_ref.so")
 REF_O0 = os.path.join(HERE, "_ref", "libmbpol_ref_O0.so")
+REF_NRG = os.path.join(HERE, "_ref", "libmbnrg_ref.so")
+ION_CODES = {"f": 1, "cl": 2, "br": 3, "i": 4, "li": 5, "na": 6, "k": 7, "rb": 8, "cs": 9}      # mbnrg.f90:541-565
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -20,8 +22,8 @@ _ip = C.POINTER(C.c_int)
 
 def build(force=False):
     """Compile the restatement (always) -- building the checker is not using it."""
-    src = os.path.join(HERE, "mbpol_oracle.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("mbpol_oracle.cpp", "mbnrg_oracle.cpp")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "libmbpol_oracle.so"])
 
 
@@ -29,7 +31,7 @@ def build_reference(fast=True):
     """Compile the reference's own evaluator sources in place (only where /root/reference exists)."""
     if not os.path.isdir("/root/reference/SOURCE"):
         return False
-    subprocess.check_call(["make", "-C", HERE, "ref-fast" if fast else "ref"])
+    subprocess.check_call(["make", "-C", HERE, "ref-fast" if fast else "ref", "ref-nrg"])
     return True
 
 
@@ -54,9 +56,52 @@ class Oracle:
                     self.ref_path = p
                     break
 
+        L.oracle_mbnrg_polyhi.restype = C.c_double
+        L.oracle_mbnrg_coef_hi.restype = _dp
+        L.oracle_mbnrg_load_reference.argtypes = [C.c_char_p]
+        self.have_nrg_reference = bool(load_reference and os.path.exists(REF_NRG) and L.oracle_mbnrg_load_reference(REF_NRG.encode()) == 0)
+
     @property
     def have_reference(self):
         return self.ref_path is not None
+
+    # ---- MB-nrg ion-water / ion-ion 2B (oracle/mbnrg_oracle.cpp) ----
+    def nrg_polyhi(self, a, x):
+        a, x, g = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(x, dtype=np.float64), np.zeros(8)
+        return self.lib.oracle_mbnrg_polyhi(_p(a), _p(x), _p(g)), g
+
+    def nrg_coef_hi(self, ion):
+        return np.ctypeslib.as_array(self.lib.oracle_mbnrg_coef_hi(int(ion)), shape=(429,)).copy()
+
+    def nrg_h2o_ion(self, ion, w, x, ref=False):
+        w, x = np.ascontiguousarray(w, dtype=np.float64), np.ascontiguousarray(x, dtype=np.float64)
+        E, g1, g2 = C.c_double(), np.zeros(9), np.zeros(3)
+        self.lib.oracle_mbnrg_h2o_ion(int(ref), int(ion), _p(w), _p(x), C.byref(E), _p(g1), _p(g2))
+        return E.value, g1, g2
+
+    def nrg_ion_ion(self, a, b, w, x, ref=False):
+        w, x = np.ascontiguousarray(w, dtype=np.float64), np.ascontiguousarray(x, dtype=np.float64)
+        E, g1, g2 = C.c_double(), np.zeros(3), np.zeros(3)
+        have = self.lib.oracle_mbnrg_ion_ion(int(ref), int(a), int(b), _p(w), _p(x), C.byref(E), _p(g1), _p(g2))
+        return bool(have), E.value, g1, g2
+
+    def nrg_forces(self, box, use_ref=False, rank=0, nranks=1):
+        """mbnrg_forces on a box dict of synth.make_ion_box: returns eng2, vir2, stress, forces and the pair counts."""
+        n = box["mxatms"]
+        f = [np.zeros(n) for _ in range(3)]
+        e, v, st, cnt = C.c_double(0.0), C.c_double(0.0), np.zeros(9), np.zeros(3, dtype=np.int64)
+        lt = np.ascontiguousarray(box["listttm2"], dtype=np.int32)
+        li = np.ascontiguousarray(box["listions"], dtype=np.int32)
+        ic = np.ascontiguousarray(box["ion_code"], dtype=np.int32)
+        cell = np.ascontiguousarray(box["cell"], dtype=np.float64)
+        rc = self.lib.oracle_mbnrg_forces(int(use_ref), int(rank), int(nranks), int(box["imcon"]), _p(cell), int(box["nttm2"]),
+                                          lt.ctypes.data_as(_ip), int(box["nions"]), li.ctypes.data_as(_ip), ic.ctypes.data_as(_ip),
+                                          _p(box["xxx"]), _p(box["yyy"]), _p(box["zzz"]), _p(f[0]), _p(f[1]), _p(f[2]),
+                                          C.byref(e), C.byref(v), _p(st), cnt.ctypes.data_as(C.POINTER(C.c_longlong)))
+        if rc:
+            raise RuntimeError("oracle_mbnrg_forces failed (%d)" % rc)
+        return dict(eng2=e.value, vir2=v.value, stress=st, fxx=f[0], fyy=f[1], fzz=f[2], npairs=int(cnt[0]), nactive=int(cnt[1]),
+                    nionion=int(cnt[2]))
 
     def ref_flags(self):
         if self.ref_path is None:
