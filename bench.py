@@ -195,6 +195,61 @@ def run_beads(args, mb, synth):
     mb.mbpol_fini(h)
 
 
+def run_ions(args, mb, synth):
+    """BASELINE config 4 (next-row f1): NaCl(aq), --nw waters + --ions Na/Cl through mbnrg_forces (ion-water + ion-ion 2B; the
+    3B term is compiled out in the reference, mbnrg.f90:4).  A "step" is one mbnrg_forces call; the unit is evaluated ion-water
+    pairs per second.  The CPU baseline is the same call through the oracle driver around the reference's evaluator objects."""
+    from mbpol_b200 import mbnrg
+    box = synth.make_ion_box(args.nw, args.ions)
+    h = mbnrg.mbnrg_init(box["nttm2"], box["ion_code"])
+    n = box["mxatms"]
+    F = [np.zeros(n) for _ in range(3)]
+    st = np.zeros(9)
+    call = lambda: mbnrg.mbnrg_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"],
+                                      box["xxx"], box["yyy"], box["zzz"], F[0], F[1], F[2], st)
+    for _ in range(max(args.warmup, 3)):
+        call()
+    t, dev = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        call()
+        t.append(time.perf_counter() - t0)
+        dev.append(mbnrg.mbnrg_kernel_times(h))
+    c = mbnrg.mbnrg_counts(h)
+    ms_dev = float(np.mean([d["total_ms"] for d in dev]))
+    ms_k = float(np.mean([d["h2o_ion_ms"] for d in dev]))
+    flop_pair = 3888                                     # multiplies + adds of the reference polynomial body per evaluated pair
+    line = {"metric": "mbnrg_ion_water_pairs_per_second", "value": c["nactive"] / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "NaCl(aq) MB-nrg 2B: %d H2O + %d Na/Cl, ion-water + ion-ion polynomials (3B compiled out in the reference)"
+                       % (box["nw"], box["nions"]), "pairs_within_10A": c["npairs"], "pairs_evaluated": c["nactive"], "ion_ion_pairs": c["nionion"],
+                       "l2": "inputs re-uploaded every step"},
+            "e2e": {"value": c["nactive"] / float(np.mean(t)), "unit": "pairs/s", "ms_per_step": 1e3 * float(np.mean(t)),
+                    "h2d_bytes_per_step": 8 * 3 * n + 4 * (box["nttm2"] + box["nions"]), "d2h_bytes_per_step": 8 * (3 * n + 16)},
+            "gpu_launches": int(dev[-1]["launches"]) * args.steps,
+            "phases_ms": {k: float(np.mean([q[k] for q in dev])) for k in ("pairs_ms", "h2o_ion_ms", "ion_ion_ms", "total_ms")},
+            "roofline": {"bound": "latency", "achieved": c["nactive"] * flop_pair / (ms_k * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s",
+                         "frac": None, "traffic": None,
+                         "note": "%d pairs x 3888 flops = %.1f MFLOP per launch: %d CTAs of 128 threads cannot fill 148 SMs; the kernel time is "
+                                 "launch + one dependent pass through a 2.4k-instruction body" % (c["nactive"], c["nactive"] * flop_pair / 1e6,
+                                                                                                   (c["nactive"] + 127) // 128)}}
+    if not args.no_cpu_baseline:
+        from oracle.oracle import Oracle
+        o = Oracle()
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            r = o.nrg_forces(box, use_ref=o.have_nrg_reference)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": r["nactive"] / dt, "unit": "pairs/s", "cores": 1, "kind": "reference" if o.have_nrg_reference else "port",
+                                "sample": "the whole step (%d calls of the oracle driver around the reference evaluator objects, %.1f ms each)"
+                                          % (reps, 1e3 * dt)}
+    print(json.dumps(line))
+    mbnrg.mbnrg_fini(h)
+
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -210,6 +265,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default=None, help="read the box from a DL_POLY CONFIG file instead of the synthetic generator")
     ap.add_argument("--beads", type=int, default=1, help="bead-batched evaluation (BASELINE config 5: --beads 32 --nw 512), 1 GPU")
+    ap.add_argument("--ions", type=int, default=0, help="MB-nrg NaCl(aq) workload (BASELINE config 4: --nw 4096 --ions 64), 1 GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -219,6 +275,8 @@ def main():
 
     import mbpol_b200 as mb
     from mbpol_b200 import synth
+    if args.ions > 0:
+        return run_ions(args, mb, synth)
     if args.config:
         from mbpol_b200 import config_io
         box = config_io.read_config(args.config)

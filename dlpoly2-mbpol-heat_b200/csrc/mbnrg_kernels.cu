@@ -5,8 +5,8 @@
 //                     and the evaluator's own cutoff test (mbnrg-2b-h2o-na-poly.cpp:224-234); ballot-compacted list of the
 //                     pairs that actually contribute
 //   N2 k_nrg_h2o_ion  one thread per listed pair: 8 variables, the 429-coefficient degree-5 polynomial as OUR shared-prefix
-//                     Horner schedule (gen/polyhi_body.inc, tools/gen_mbnrg.py; 2 411 FP64 instructions against ~6.9k flops
-//                     of the Maple-generated reference body), chain rule, switch, scatter             (mbnrg-2b-h2o-na-poly.cpp:220-329,
+//                     Horner schedule (gen/polyhi_body.inc, tools/gen_mbnrg.py; 2 411 FP64 instructions, 2 128 of them FMAs, against the 3 888
+//                     multiplies and adds of the Maple-generated reference body), chain rule, switch, scatter             (mbnrg-2b-h2o-na-poly.cpp:220-329,
 //                     mbnrg.f90:706-775)
 //   N3 k_nrg_ion_ion  one thread per ion pair j < k                                                 (mbnrg-2b-na-cl-poly.cpp:129-186)
 // Scalars (energy, virial, stress) are block-reduced before one FP64 atomic per block; forces use FP64 red.global.add.
