@@ -869,7 +869,7 @@ int mbpol_b200_init(int nttm2, int device, int flags, mbpol_b200_handle** handle
 
 int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_b200_handle** handle)
 {
-    if (!handle || nttm2 < 3 || nttm2 % 3 || nbeads < 1 || (long long)nbeads * nttm2 > 0x3fffffffLL) return MBPOL_B200_EINVAL;
+    if (!handle || nttm2 < 0 || nttm2 % 3 || nbeads < 1 || (long long)nbeads * nttm2 > 0x3fffffffLL) return MBPOL_B200_EINVAL;
     *handle = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MBPOL_B200_ENODEVICE;
@@ -1003,6 +1003,13 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
 
     CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
     CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_count() * 8, s));
+    if (nw == 0) {   // no water at all (the reference's loops simply do not execute): zero contributions, nothing to launch
+        h->nd_total = h->nt_total = h->nd_shard = h->nt_shard = 0;
+        for (int k = 1; k < 5; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        for (float& m : h->ms) m = 0.f;
+        return MBPOL_B200_OK;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->cell_cnt.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->cell_fill.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->flag.p, 0, 4, s));

@@ -60,6 +60,6 @@ def test_fails_loudly_without_gpu():
 def test_init_argument_checks():
     lib = mb.load_library()
     p = C.c_void_p()
-    assert lib.mbpol_b200_init(0, -1, 3, C.byref(p)) == 1        # EINVAL: nttm2 < 3
+    assert lib.mbpol_b200_init(-3, -1, 3, C.byref(p)) == 1       # EINVAL: negative nttm2 (0 waters is a legal, empty system)
     assert lib.mbpol_b200_init(10, -1, 3, C.byref(p)) == 1       # EINVAL: not a multiple of 3
     assert lib.mbpol_b200_fini(None) == 1

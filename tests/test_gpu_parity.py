@@ -309,5 +309,66 @@ mb.mbpol_fini(h)
 print("engine ok")
 ''' % (ROOT_DIR, os.path.join(ROOT_DIR, "tests"))
     env = dict(os.environ, MBPOL_B200_ENGINE=engine)
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "engine ok" in r.stdout, r.stdout + r.stderr
+
+
+def small_system(positions, L=30.0):
+    """nw rigid waters with their oxygens at `positions` (a hand-made cluster in a big cubic box)."""
+    w0 = np.array([[0.0, 0.0, 0.0], [0.9572, 0.0, 0.0], [-0.24, 0.9266, 0.0]])
+    nw = len(positions)
+    xyz = np.zeros((4 * max(nw, 1), 3))
+    for m, p in enumerate(positions):
+        xyz[3 * m:3 * m + 3] = w0 + np.asarray(p, dtype=float)
+    cell = np.zeros(9)
+    cell[0] = cell[4] = cell[8] = L
+    return {"nw": nw, "mxatms": len(xyz), "nttm2": 3 * nw, "imcon": 1, "cell": cell, "L": L,
+            "listttm2": np.arange(1, 3 * nw + 1, dtype=np.int32), "xxx": np.ascontiguousarray(xyz[:, 0]),
+            "yyy": np.ascontiguousarray(xyz[:, 1]), "zzz": np.ascontiguousarray(xyz[:, 2]),
+            "vxx": np.zeros(len(xyz)), "vyy": np.zeros(len(xyz)), "vzz": np.zeros(len(xyz))}
+
+
+@pytest.mark.parametrize("positions,nd,nt", [
+    ([], 0, 0),                                                        # empty system
+    ([(0, 0, 0)], 0, 0),                                               # one water: no cluster at all
+    ([(0, 0, 0), (2.9, 0.3, 0.1)], 1, 0),                              # one dimer, no trimer
+    ([(0, 0, 0), (8.0, 0, 0)], 0, 0),                                  # beyond the 2B cutoff
+    ([(0, 0, 0), (2.9, 0.3, 0.1), (1.2, 2.7, 0.4)], 3, 1),             # closed triangle: one trimer
+    ([(0, 0, 0), (3.0, 0, 0), (7.0, 0.2, 0)], 2, 1),                   # chain: 0-2 is 7 A apart (no dimer), trimer via the centre water
+    ([(0, 0, 0), (4.4, 0, 0), (9.1, 0, 0)], 2, 0),                     # 1-2 at 4.7 A: inside r2f, outside r3f -> no trimer
+])
+def test_degenerate_systems(mb, oracle, positions, nd, nt):
+    """Empty and tiny inputs (the reference's loops simply do not execute): counts, energies and forces against the oracle."""
+    box = small_system(positions)
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    out = mb.run_box(h, box, want_stress=True)
+    c = mb.mbpol_counts(h)
+    mb.mbpol_fini(h)
+    assert (c["dimers"], c["trimers"]) == (nd, nt)
+    if box["nw"] == 0:
+        assert out["eng2"] == 0.0 and out["eng3"] == 0.0 and not np.any(out["fxx"])
+        return
+    ref = oracle.forces(box, mode="listed", use_ref=oracle.have_reference, nthreads=1)
+    assert (ref["ndimer"], ref["ntrimer"]) == (nd, nt)
+    for k in ("eng2", "vir2", "eng3", "vir3"):
+        assert abs(out[k] - ref[k]) <= E_TOL * max(abs(ref[k]), 1e-300), k
+    if nd:      # planar clusters: a component can vanish by symmetry, so scale by the largest force / tensor entry
+        fmax = max(np.abs(ref[k]).max() for k in ("fxx", "fyy", "fzz"))
+        for k in ("fxx", "fyy", "fzz"):
+            assert np.abs(out[k] - ref[k]).max() <= F_TOL * fmax, k
+        for k in ("atomic_energy", "atomic_fdecomp", "atomic_stress", "stress"):
+            assert np.abs(out[k] - ref[k]).max() <= F_TOL * np.abs(ref[k]).max(), k
+    else:
+        assert not np.any(out["fxx"]) and not np.any(out["atomic_energy"])
+
+
+def test_unphysical_density_is_reported_not_truncated(mb):
+    """More neighbours than the per-water row capacity: the call must fail with ECAPACITY, never drop clusters silently."""
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(0.0, 4.0, size=(300, 3))             # 300 waters inside a 4 A cube
+    box = small_system(pos, L=40.0)
+    h = mb.mbpol_init(box["nttm2"], flags=3)
+    with pytest.raises(mb.MBPolError) as e:
+        mb.run_box(h, box)
+    assert "status 3" in str(e.value)
+    mb.mbpol_fini(h)
