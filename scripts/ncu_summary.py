@@ -29,6 +29,8 @@ ix = {h: i for i, h in enumerate(hdr)}
 agg = collections.defaultdict(collections.Counter)
 tot = 0
 for r in rows[hi + 1:]:
+    if len(r) < len(hdr) or r[0] == "Address":      # a second kernel section / trailer in the CSV
+        continue
     toks = r[ix["Source"]].split()
     if not toks:
         continue
