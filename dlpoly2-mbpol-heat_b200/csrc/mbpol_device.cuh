@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include "gen/poly_gen.h"
 #include "mbpol_tape.cuh"
+#include "mbpol_fat.cuh"
 
 // linear coefficients: referenced by name from the generated PTX (.extern .const)
 extern __constant__ double mbpol_cwin[];   // the single constant-bank window: PTX-engine coefficient tables or one tape window
@@ -163,8 +164,9 @@ __device__ __forceinline__ void trimer_finish(const double* xv, const double* gp
 template <int ENGINE>
 __device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
 {
-    double xv[ENGINE == 1 ? 36 : POLY3B_RECORD_DOUBLES], gp_[ENGINE == 1 ? 36 : 1];
-    double* gp = ENGINE == 1 ? gp_ : xv + 37;      // ENGINE 0/2: x and g live in the per-thread record (local memory)
+    constexpr bool SMEM_TAPE = ENGINE == 1 || ENGINE == 3;     // engines that walk a shared-memory tape: x[], g[] in registers
+    double xv[SMEM_TAPE ? 36 : POLY3B_RECORD_DOUBLES], gp_[SMEM_TAPE ? 36 : 1];
+    double* gp = SMEM_TAPE ? gp_ : xv + 37;      // ENGINE 0/2: x and g live in the per-thread record (local memory)
     double rinv[36];
     trimer_variables(r, xv, rinv);
     double Epoly;
@@ -174,6 +176,9 @@ __device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, do
     } else if (ENGINE == 2) {
         if (!cpass_step<36>(xv, ctx)) return false;
         Epoly = xv[36];
+    } else if (ENGINE == 3) {
+        fat_eval<36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
+                     *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
     } else {
         tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
                          *reinterpret_cast<TapeSmem<36>*>(ctx.smem));

@@ -36,6 +36,9 @@ __constant__ unsigned c_tape_segs2b[TAPE2B_NSEGS];
 __constant__ unsigned c_tape_segs3b[TAPE3B_NSEGS];
 __constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][3];
 __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
+__constant__ unsigned c_fat_rowvars3b[FAT3B_NROWS + 1];
+__constant__ unsigned c_fat_segs3b[FAT3B_NSEGS];
+__constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
 
 namespace {
 
@@ -662,6 +665,7 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 std::once_flag g_const_once[16];
 double* g_tape2b[16] = {nullptr};
 double* g_tape3b[16] = {nullptr};
+double* g_fat3b[16] = {nullptr};      // engine 3: the 3B coefficients in fat-row order
 double* g_coefwin[16] = {nullptr};
 
 // (re)fill the constant-bank window, ordered on `s` behind the kernels that read the previous content
@@ -683,10 +687,11 @@ cudaError_t load_pass_window(int device, int which, int p, cudaStream_t s)
 }
 cudaError_t load_coef_window(int device, cudaStream_t s) { return load_window(g_coefwin[device], MBPOL_NCOEF2B + MBPOL_NCOEF3B, s); }
 
-// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory, 2 = coefficient tape in
-// the constant bank (3B in NCPASS launches; 2B uses engine 1).  MBPOL_B200_ENGINE=ptx|tape|ctape overrides the default.
+// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory (rows), 2 = coefficient tape in
+// the constant bank (3B in NCPASS launches; 2B uses engine 1), 3 = shared-memory tape with FAT rows (3B; 2B uses engine 1).
+// MBPOL_B200_ENGINE=ptx|tape|ctape|fat overrides the default.
 #ifndef MBPOL_DEFAULT_ENGINE
-#define MBPOL_DEFAULT_ENGINE 1
+#define MBPOL_DEFAULT_ENGINE 3
 #endif
 int default_engine()
 {
@@ -694,6 +699,7 @@ int default_engine()
     if (e && std::string(e) == "ptx") return 0;
     if (e && std::string(e) == "tape") return 1;
     if (e && std::string(e) == "ctape") return 2;
+    if (e && std::string(e) == "fat") return 3;
     return MBPOL_DEFAULT_ENGINE;
 }
 constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM2C = sizeof(TapeCSmem<31>), SMEM3C = sizeof(TapeCSmem<36>);
@@ -751,6 +757,14 @@ int upload_constants(int device)
         if (cudaMemcpy(d2, t2.data(), t2.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
         if (cudaMemcpy(d3, t3.data(), t3.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
         g_tape2b[device] = d2; g_tape3b[device] = d3;
+        std::vector<double> tf(FAT3B_NTAPE);               // engine 3: the same coefficients in fat-row order
+        for (int i = 0; i < FAT3B_NTAPE; ++i) tf[i] = FAT3B_COEFIDX_HOST[i] < 0 ? 0.0 : MBPOL_COEF3B_HOST[FAT3B_COEFIDX_HOST[i]];
+        double* df = nullptr;
+        if (cudaMalloc(&df, tf.size() * 8) != cudaSuccess || cudaMemcpy(df, tf.data(), tf.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        g_fat3b[device] = df;
+        if (cudaMemcpyToSymbol(c_fat_rowvars3b, FAT3B_ROWVARS_HOST, sizeof(FAT3B_ROWVARS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_fat_segs3b, FAT3B_SEGS_HOST, sizeof(FAT3B_SEGS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_fat_chunks3b, FAT3B_CHUNKS_HOST, sizeof(FAT3B_CHUNKS_HOST)) != cudaSuccess) return 1;
         std::vector<TapeCPassHeader> h2(TAPE2B_NCPASS), h3(TAPE3B_NCPASS);
         for (int p = 0; p < TAPE2B_NCPASS; ++p)
             h2[p] = {TAPE2B_CPASS_HOST[p][0], TAPE2B_CPASS_HOST[p + 1][0], (unsigned)TAPE2B_CPASS_HOST[p][1], (unsigned)TAPE2B_CPASS_HOST[p + 1][1] - 1u};
@@ -881,7 +895,7 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
     h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine();
-    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
+    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess ||
         allow_smem(k_dimers<2>, SMEM2C) != cudaSuccess || allow_smem(k_trimers<2>, SMEM3C) != cudaSuccess) {
         delete h;
         return MBPOL_B200_ECUDA;
@@ -1060,7 +1074,7 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
                 ++h->launches;
             }
             --h->launches;
-        } else if (h->engine == 1) {
+        } else if (h->engine == 1 || h->engine == 3) {      // the fat engine exists for the 3B polynomial only
             k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device], nullptr, true, true);
         } else {
             CUDA_TRY(h, load_coef_window(h->device, s));
@@ -1081,6 +1095,8 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
                 ++h->launches;
             }
             --h->launches;
+        } else if (h->engine == 3) {
+            k_trimers<3><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat3b[h->device], nullptr, true, true);
         } else if (h->engine == 1) {
             k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device], nullptr, true, true);
         } else {
@@ -1258,13 +1274,14 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
     if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
         const int eng = default_engine();
-        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); }
+        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); }
         else ok(load_coef_window(device, 0));
         if (nat3 == 18) {
             if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);   // engine 2 -> 1 here
             else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
         } else {
-            if (eng) k_eval_trimers<1><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
+            if (eng == 3) k_eval_trimers<3><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
+            else if (eng) k_eval_trimers<1><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
             else k_eval_trimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
         }
         ok(cudaGetLastError());

@@ -85,3 +85,41 @@ def test_tape_rows_reproduce_the_polynomials(oracle):
         assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
         assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()
         assert len(types) <= 64 and max(len(v) for v in by_id.values()) <= nv
+
+
+def test_fat_rows_reproduce_the_3b_polynomial(oracle):
+    """tools/gen_fat.py: the fat rows of engine 3 (all rows sharing the (w,v) prefix merged; children (u, leaf set) static)
+    are the same polynomial and gradient as the monomial table -- checked in numpy from the generator's own structures,
+    following exactly the arithmetic of the generated code (T = sum_k S_k x_u, E += T p2, g_u += S_k p2, ...)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_fat
+    import gen_poly
+    d = np.load(gen_poly.DATA)
+    nv = 36
+    fat, shapes = gen_fat.build("3b", d["mono3b"], nv, "reverse")
+    assert len(fat) == 361 and len(shapes) <= 64 and len(set((w, v) for (_, w, v, _) in fat)) == len(fat)
+    a = oracle.coef("3b")
+    rng = np.random.default_rng(12)
+    x = rng.uniform(0.1, 1.2, size=nv)
+    xe = np.concatenate([x, [1.0]])
+    E, g = 0.0, np.zeros(nv + 1)
+    nmono = 0
+    for (s, w, v, ch) in fat:
+        assert tuple((c[0], c[1]) for c in ch) == shapes[s]
+        p2 = xe[w] * xe[v]
+        Tw = 0.0
+        for (u, ls, own, cs) in ch:
+            P = p2 * xe[u]
+            S = (a[own] if own >= 0 else 0.0) + sum(a[k] * x[c] for k, c in zip(cs, ls))
+            for k, c in zip(cs, ls):
+                g[c] += a[k] * P
+            g[u] += S * p2
+            Tw += S * xe[u]
+            nmono += len(cs) + (own >= 0)
+        E += Tw * p2
+        g[w] += Tw * xe[v]
+        g[v] += Tw * xe[w]
+    assert nmono == len(d["mono3b"])
+    Er, gr = oracle.poly("3b", a, x)
+    assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+    assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()
