@@ -177,7 +177,7 @@ __device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, do
         if (!cpass_step<36>(xv, ctx)) return false;
         Epoly = xv[36];
     } else if (ENGINE == 3) {
-        fat_eval<36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
+        fat_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
                      *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
     } else {
         tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
@@ -266,12 +266,13 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     if (fm)
         for (int i = 0; i < 108; ++i) fm[i] = 0.0;
     const bool inside = !(rOO > mbpol_par.r2f);
-    if (ENGINE != 1 && !inside && (ENGINE == 0 || ctx.last)) return false;   // engine 1 has CTA barriers: every thread walks on
+    constexpr bool SMEM_TAPE = ENGINE == 1 || ENGINE == 3;     // engines that walk a shared-memory tape with CTA barriers
+    if (!SMEM_TAPE && !inside && (ENGINE == 0 || ctx.last)) return false;   // those have CTA barriers: every thread walks on
     lonepair_sites(xc + 0, xc + 18, xc + 21);
     lonepair_sites(xc + 9, xc + 24, xc + 27);
 
-    double xv[ENGINE == 1 ? 31 : POLY2B_RECORD_DOUBLES], gp_[ENGINE == 1 ? 31 : 1];
-    double* gp = ENGINE == 1 ? gp_ : xv + 32;
+    double xv[SMEM_TAPE ? 31 : POLY2B_RECORD_DOUBLES], gp_[SMEM_TAPE ? 31 : 1];
+    double* gp = SMEM_TAPE ? gp_ : xv + 32;
     double gfac[31];    // dv/dr / r : the variable's gradient is gfac * (r_a - r_b)
 #pragma unroll
     for (int n = 0; n < 31; ++n) {
@@ -298,6 +299,9 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     } else if (ENGINE == 2) {
         if (!cpass_step<31>(xv, ctx)) return false;
         Epoly = xv[31];
+    } else if (ENGINE == 3) {
+        fat_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,
+                        *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
     } else {
         tape_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,
                          *reinterpret_cast<TapeSmem<31>*>(ctx.smem));

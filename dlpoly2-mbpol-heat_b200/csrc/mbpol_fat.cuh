@@ -7,11 +7,15 @@
 // per-thread shared-memory columns for the dynamic x / g accesses), one counted loop per (chunk, shape) segment.
 #pragma once
 #include "mbpol_tape.cuh"
+#include "gen/fat_2b.h"
 #include "gen/fat_3b.h"
 
 static_assert(FAT_CHUNK_DOUBLES == TAPE_CHUNK_DOUBLES, "engines 1 and 3 share the staging buffers");
+extern __constant__ unsigned c_fat_rowvars2b[FAT2B_NROWS + 1];
 extern __constant__ unsigned c_fat_rowvars3b[FAT3B_NROWS + 1];
+extern __constant__ unsigned c_fat_segs2b[FAT2B_NSEGS];
 extern __constant__ unsigned c_fat_segs3b[FAT3B_NSEGS];
+extern __constant__ int c_fat_chunks2b[FAT2B_NCHUNKS + 1][3];
 extern __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
 
 #define FAT_ROW_LOOP(nrows) _Pragma("unroll 1") for (unsigned r_ = 0; r_ < (nrows); ++r_)
@@ -37,12 +41,15 @@ extern __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
     cp += (ROWBYTES);                                                                                    \
     ++row;
 
-// x -> E = poly3b(x), g = dE/dx.  Must be called by ALL threads of a TAPE_BS-wide CTA (it contains barriers).
-template <int NV>
+// x -> E = poly(x), g = dE/dx.  Must be called by ALL threads of a TAPE_BS-wide CTA (it contains barriers).
+template <int WHICH, int NV>
 __device__ __forceinline__ void fat_eval(const double* __restrict__ tape, double (&x)[NV], double (&g)[NV], double& E, TapeSmem<NV>& sm)
 {
-    static_assert(NV == FAT3B_NV, "the fat engine is generated for the 3B polynomial");
-    const unsigned* rowvars = c_fat_rowvars3b;
+    static_assert(NV == (WHICH == 3 ? FAT3B_NV : FAT2B_NV), "polynomial / variable count mismatch");
+    constexpr int nchunks = (WHICH == 3) ? FAT3B_NCHUNKS : FAT2B_NCHUNKS;
+    const unsigned* rowvars = (WHICH == 3) ? c_fat_rowvars3b : c_fat_rowvars2b;
+    const unsigned* segs = (WHICH == 3) ? c_fat_segs3b : c_fat_segs2b;
+    const int(*chunks)[3] = (WHICH == 3) ? c_fat_chunks3b : c_fat_chunks2b;
     const unsigned tid = threadIdx.x;
     const unsigned buf0 = (unsigned)__cvta_generic_to_shared(&sm.buf[0][0]);
     const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
@@ -56,15 +63,15 @@ __device__ __forceinline__ void fat_eval(const double* __restrict__ tape, double
     tape_sts(xs_t + NV * TAPE_COL, 1.0);
     tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
     auto stage = [&](int k) {
-        const int t0 = c_fat_chunks3b[k][2], n = c_fat_chunks3b[k + 1][2] - t0;      // both even: 16-byte granules
+        const int t0 = chunks[k][2], n = chunks[k + 1][2] - t0;      // both even: 16-byte granules
         const unsigned dst = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
         for (int i = 2 * tid; i < n; i += 2 * TAPE_BS) tape_cp_async16(dst + 8 * i, tape + t0 + i);
         tape_cp_commit();
     };
     stage(0);
     double e = 0.0;
-    for (int k = 0; k < FAT3B_NCHUNKS; ++k) {
-        if (k + 1 < FAT3B_NCHUNKS) {
+    for (int k = 0; k < nchunks; ++k) {
+        if (k + 1 < nchunks) {
             stage(k + 1);
             tape_cp_wait<1>();
         } else {
@@ -72,15 +79,19 @@ __device__ __forceinline__ void fat_eval(const double* __restrict__ tape, double
         }
         __syncthreads();                                   // chunk k visible to every thread
         unsigned cp = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
-        unsigned row = c_fat_chunks3b[k][1];
-        const int sg1 = c_fat_chunks3b[k + 1][0];
+        unsigned row = chunks[k][1];
+        const int sg1 = chunks[k + 1][0];
         unsigned nw_, nv_;
         double nxw, nxv;
         FAT_ROW_FETCH(row)
-        for (int sg = c_fat_chunks3b[k][0]; sg < sg1; ++sg) {
-            const unsigned seg = c_fat_segs3b[sg];
+        for (int sg = chunks[k][0]; sg < sg1; ++sg) {
+            const unsigned seg = segs[sg];
             const unsigned shape = seg & 255u, nrows = seg >> 8;
-            FAT3B_SEGMENT_SWITCH(shape, nrows)
+            if constexpr (WHICH == 3) {
+                FAT3B_SEGMENT_SWITCH(shape, nrows)
+            } else {
+                FAT2B_SEGMENT_SWITCH(shape, nrows)
+            }
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }

@@ -36,8 +36,11 @@ __constant__ unsigned c_tape_segs2b[TAPE2B_NSEGS];
 __constant__ unsigned c_tape_segs3b[TAPE3B_NSEGS];
 __constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][3];
 __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
+__constant__ unsigned c_fat_rowvars2b[FAT2B_NROWS + 1];
 __constant__ unsigned c_fat_rowvars3b[FAT3B_NROWS + 1];
+__constant__ unsigned c_fat_segs2b[FAT2B_NSEGS];
 __constant__ unsigned c_fat_segs3b[FAT3B_NSEGS];
+__constant__ int c_fat_chunks2b[FAT2B_NCHUNKS + 1][3];
 __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
 
 namespace {
@@ -665,7 +668,8 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 std::once_flag g_const_once[16];
 double* g_tape2b[16] = {nullptr};
 double* g_tape3b[16] = {nullptr};
-double* g_fat3b[16] = {nullptr};      // engine 3: the 3B coefficients in fat-row order
+double* g_fat3b[16] = {nullptr};      // engine 3: the coefficients in fat-row order
+double* g_fat2b[16] = {nullptr};
 double* g_coefwin[16] = {nullptr};
 
 // (re)fill the constant-bank window, ordered on `s` behind the kernels that read the previous content
@@ -688,7 +692,7 @@ cudaError_t load_pass_window(int device, int which, int p, cudaStream_t s)
 cudaError_t load_coef_window(int device, cudaStream_t s) { return load_window(g_coefwin[device], MBPOL_NCOEF2B + MBPOL_NCOEF3B, s); }
 
 // polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory (rows), 2 = coefficient tape in
-// the constant bank (3B in NCPASS launches; 2B uses engine 1), 3 = shared-memory tape with FAT rows (3B; 2B uses engine 1).
+// the constant bank (3B in NCPASS launches; 2B uses engine 1), 3 = shared-memory tape with FAT rows.
 // MBPOL_B200_ENGINE=ptx|tape|ctape|fat overrides the default.
 #ifndef MBPOL_DEFAULT_ENGINE
 #define MBPOL_DEFAULT_ENGINE 3
@@ -701,6 +705,18 @@ int default_engine()
     if (e && std::string(e) == "ctape") return 2;
     if (e && std::string(e) == "fat") return 3;
     return MBPOL_DEFAULT_ENGINE;
+}
+// the 2B polynomial may use another engine than the 3B one (MBPOL_B200_ENGINE_2B=ptx|tape|fat; ctape falls back to tape)
+#ifndef MBPOL_DEFAULT_ENGINE_2B
+#define MBPOL_DEFAULT_ENGINE_2B 1   /* measured: rows 3.6-3.8 ms, fat rows 4.05 ms for the 2B polynomial (521 fat rows of 27 shapes merge only 2 rows each) */
+#endif
+int default_engine_2b(int engine3b)
+{
+    const char* e = std::getenv("MBPOL_B200_ENGINE_2B");
+    if (e && std::string(e) == "ptx") return 0;
+    if (e && std::string(e) == "tape") return 1;
+    if (e && std::string(e) == "fat") return 3;
+    return std::getenv("MBPOL_B200_ENGINE") ? engine3b : MBPOL_DEFAULT_ENGINE_2B;
 }
 constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM2C = sizeof(TapeCSmem<31>), SMEM3C = sizeof(TapeCSmem<36>);
 
@@ -762,6 +778,14 @@ int upload_constants(int device)
         double* df = nullptr;
         if (cudaMalloc(&df, tf.size() * 8) != cudaSuccess || cudaMemcpy(df, tf.data(), tf.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
         g_fat3b[device] = df;
+        std::vector<double> tf2(FAT2B_NTAPE);
+        for (int i = 0; i < FAT2B_NTAPE; ++i) tf2[i] = FAT2B_COEFIDX_HOST[i] < 0 ? 0.0 : MBPOL_COEF2B_HOST[FAT2B_COEFIDX_HOST[i]];
+        double* df2 = nullptr;
+        if (cudaMalloc(&df2, tf2.size() * 8) != cudaSuccess || cudaMemcpy(df2, tf2.data(), tf2.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        g_fat2b[device] = df2;
+        if (cudaMemcpyToSymbol(c_fat_rowvars2b, FAT2B_ROWVARS_HOST, sizeof(FAT2B_ROWVARS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_fat_segs2b, FAT2B_SEGS_HOST, sizeof(FAT2B_SEGS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_fat_chunks2b, FAT2B_CHUNKS_HOST, sizeof(FAT2B_CHUNKS_HOST)) != cudaSuccess) return 1;
         if (cudaMemcpyToSymbol(c_fat_rowvars3b, FAT3B_ROWVARS_HOST, sizeof(FAT3B_ROWVARS_HOST)) != cudaSuccess) return 1;
         if (cudaMemcpyToSymbol(c_fat_segs3b, FAT3B_SEGS_HOST, sizeof(FAT3B_SEGS_HOST)) != cudaSuccess) return 1;
         if (cudaMemcpyToSymbol(c_fat_chunks3b, FAT3B_CHUNKS_HOST, sizeof(FAT3B_CHUNKS_HOST)) != cudaSuccess) return 1;
@@ -817,7 +841,7 @@ struct DevBuf {
 }  // namespace
 
 struct mbpol_b200_handle {
-    int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1, engine = 1;
+    int device = 0, nw = 0, flags = 0, rank = 0, nranks = 1, engine = 1, engine2b = 1;
     int nbeads = 1, nwb = 0, mxb = 0;      // bead-batched calls: nw = nbeads*nwb waters, mxatms = nbeads*mxb atoms
     int mxatms = 0, imcon = 0;
     bool have_vel = false, uploaded = false;
@@ -894,8 +918,8 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     if (cudaSetDevice(device) != cudaSuccess) return MBPOL_B200_ECUDA;
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
-    h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine();
-    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess ||
+    h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine(); h->engine2b = default_engine_2b(h->engine);
+    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_dimers<3>, SMEM2B) != cudaSuccess ||
         allow_smem(k_dimers<2>, SMEM2C) != cudaSuccess || allow_smem(k_trimers<2>, SMEM3C) != cudaSuccess) {
         delete h;
         return MBPOL_B200_ECUDA;
@@ -1065,7 +1089,7 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     if (h->nd_shard > 0) {
         const unsigned gd = (unsigned)((h->nd_shard + 255) / 256);
         const int2* dl = h->dimers.p + d0;
-        if (h->engine == 2) {
+        if (h->engine2b == 2) {
             CUDA_TRY(h, h->gbuf.reserve((size_t)37 * std::max(h->nt_shard, h->nd_shard)));
             for (int p = 0; p < TAPE2B_NCPASS; ++p) {
                 CUDA_TRY(h, load_pass_window(h->device, 2, p, s));
@@ -1074,7 +1098,9 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
                 ++h->launches;
             }
             --h->launches;
-        } else if (h->engine == 1 || h->engine == 3) {      // the fat engine exists for the 3B polynomial only
+        } else if (h->engine2b == 3) {
+            k_dimers<3><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device], nullptr, true, true);
+        } else if (h->engine2b == 1) {
             k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device], nullptr, true, true);
         } else {
             CUDA_TRY(h, load_coef_window(h->device, s));
@@ -1274,10 +1300,11 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
     if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
         const int eng = default_engine();
-        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); }
+        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B)); }
         else ok(load_coef_window(device, 0));
         if (nat3 == 18) {
-            if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);   // engine 2 -> 1 here
+            if (eng == 3) k_eval_dimers<3><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
+            else if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);   // engine 2 -> 1 here
             else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
         } else {
             if (eng == 3) k_eval_trimers<3><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);

@@ -50,7 +50,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-CWINDOW = 5376        # doubles of the shared constant-bank window (see tools/gen_tape.py)
+CWINDOW = 5248        # doubles of the shared constant-bank window (see tools/gen_tape.py)
 DATA = os.path.join(ROOT, "dlpoly2-mbpol-heat_b200", "data", "mbpol_model.npz")
 OUTD = os.path.join(ROOT, "dlpoly2-mbpol-heat_b200", "csrc", "gen")
 
