@@ -35,7 +35,7 @@ import gen_poly as G
 
 OUTD = G.OUTD
 CHUNK = 2048          # doubles per staged tape chunk (16 KB), shared-memory tape engine (1024: +2 %, 4096: +7 % time)
-CWINDOW = G.CWINDOW    # doubles of the constant-bank window (42 KB), constant tape engine
+CWINDOW = G.CWINDOW    # doubles of the constant-bank window (41 KB), constant tape engine
 NPF = 4               # tape pairs of the NEXT row prefetched by every row (software pipelining across rows)
 PAIR = False          # see emit_header
 NSUM = 2              # independent partial sums of the Horner accumulator S (shortens the dependent DFMA chain)
