@@ -860,6 +860,7 @@ struct mbpol_b200_handle {
     std::vector<int> host_list;
     double* pinned = nullptr;
     size_t pinned_cap = 0;
+    std::vector<cudaEvent_t> dl_ev;            // one event behind every piece of the pipelined download
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
     float ms[4] = {0, 0, 0, 0};
     size_t out_count() const { return (size_t)22 * mxatms + (size_t)NSCAL * nbeads; }
@@ -937,6 +938,7 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     cudaStreamSynchronize(h->stream);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (cudaEvent_t e : h->dl_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
     return MBPOL_B200_OK;
@@ -1159,25 +1161,41 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         h->pinned_cap = cnt;
     }
     double* P = h->pinned;
-    // copy only what the caller asked for
-    CUDA_TRY(h, cudaMemcpyAsync(P, h->out.p, (atomic_energy ? 4 : 3) * n * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (atomic_stress) CUDA_TRY(h, cudaMemcpyAsync(P + 4 * n, h->out.p + 4 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (atomic_fdecomp) CUDA_TRY(h, cudaMemcpyAsync(P + 13 * n, h->out.p + 13 * n, 9 * n * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    // accumulate into the caller's arrays (the reference's "+=" semantics); a few host threads for the 22*mxatms adds
-    struct Job { double* dst; const double* src; size_t len; };
-    std::vector<Job> jobs = {{fxx, P, n}, {fyy, P + n, n}, {fzz, P + 2 * n, n}};
-    if (atomic_energy) jobs.push_back({atomic_energy, P + 3 * n, n});
-    if (atomic_stress) jobs.push_back({atomic_stress, P + 4 * n, 9 * n});
-    if (atomic_fdecomp) jobs.push_back({atomic_fdecomp, P + 13 * n, 9 * n});
+    // Copy only what the caller asked for, in pieces with an event behind each piece: the host threads accumulate piece k
+    // into the caller's arrays (the reference's "+=" semantics) while piece k+1 is still crossing PCIe.
+    struct Job { double* dst; size_t off, len; };
+    std::vector<Job> jobs = {{fxx, 0, n}, {fyy, n, n}, {fzz, 2 * n, n}};
+    if (atomic_energy) jobs.push_back({atomic_energy, 3 * n, n});
+    for (int half = 0; half < 2; ++half) {
+        const size_t a = 9 * n * half / 2, b = 9 * n * (half + 1) / 2;
+        if (atomic_stress) jobs.push_back({atomic_stress + a, 4 * n + a, b - a});
+    }
+    for (int half = 0; half < 2; ++half) {
+        const size_t a = 9 * n * half / 2, b = 9 * n * (half + 1) / 2;
+        if (atomic_fdecomp) jobs.push_back({atomic_fdecomp + a, 13 * n + a, b - a});
+    }
+    while (h->dl_ev.size() < jobs.size() + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->dl_ev.push_back(e);
+    }
     size_t total = 0;
-    for (auto& j : jobs) total += j.len;
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        CUDA_TRY(h, cudaMemcpyAsync(P + jobs[k].off, h->out.p + jobs[k].off, jobs[k].len * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->dl_ev[k], h->stream));
+        total += jobs[k].len;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
     const unsigned nth = total < (1u << 18) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
     auto work = [&](unsigned t) {
-        for (auto& j : jobs) {
+        cudaSetDevice(h->device);
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            cudaEventSynchronize(h->dl_ev[k]);
+            const Job& j = jobs[k];
+            const double* src = P + j.off;
             const size_t a = j.len * t / nth, b = j.len * (t + 1) / nth;
-            for (size_t i = a; i < b; ++i) j.dst[i] += j.src[i];
+            for (size_t i = a; i < b; ++i) j.dst[i] += src[i];
         }
     };
     if (nth == 1) work(0);
@@ -1187,6 +1205,7 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         work(0);
         for (auto& t : th) t.join();
     }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int b = 0; b < h->nbeads; ++b) {     // scalars are per bead: eng2[b], ..., stress[9*b + q], jflux[9*b + q]
         const double* sc = P + 22 * n + (size_t)b * NSCAL;
         if (eng2) eng2[b] += sc[S_ENG2];
