@@ -1,12 +1,14 @@
 // mbpol_tape.cuh -- the "coefficient tape" polynomial engine (see tools/gen_tape.py for the format and the why).
 //
-// The polynomial is a list of independent ROWS sorted by type (= leaf-variable set):
+// The polynomial is a list of independent ROWS sorted by (type = leaf-variable set, u, w, v):
 //     P = x_u x_w x_v,  S = own + sum_c a_c x_c,  E += S P,  g_c += a_c P,  g_u += S x_w x_v,  g_w += S x_u x_v,  g_v += S x_u x_w.
 // One thread owns one cluster; all 256 threads of the CTA walk the SAME rows in lock step.  Engine 1 (this part of the
-// file): the coefficient tape is staged global -> shared once per CTA with cp.async (double buffered 16 KB chunks) and read
-// with broadcast LDS.128; one small counted loop per (chunk, type) segment, static register names for x[], g[]; the
-// (u,w,v) word of a row comes from constant memory; dynamic-index reads of x and updates of g go through per-thread
-// columns in shared memory (32-bit shared addresses).  Engine 2 (second half): the tape is read from the constant bank.
+// file; default for the 2B polynomial): the coefficient tape is staged global -> shared once per CTA with cp.async (double
+// buffered 16 KB chunks) and read with broadcast LDS.128; one small counted loop per (chunk, type, u) segment with x_u and
+// the segment's g_u sum in registers, static register names for x[], g[]; the (w,v) word of a row comes from constant
+// memory; dynamic-index reads of x and updates of g go through per-thread columns in shared memory (32-bit shared
+// addresses).  Engine 2 (second half): the tape is read from the constant bank.  Engine 3 (mbpol_fat.cuh, default for the
+// 3B polynomial): the same machinery with all rows of one (w,v) prefix merged into a fat row.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -20,9 +20,10 @@ Rows.  Every trie node with leaf children is one independent ROW
       (type t, u, w, v, own, a_1..a_n):   P = x_u x_w x_v,  S = own + sum_c a_c x_c,
       E += S*P;  g_c += a_c*P (c in the row's static variable set);  g_u += S x_w x_v;  g_w += S x_u x_v;  g_v += S x_u x_w
 (missing levels use a pseudo-variable UNIT = NV that is identically 1 and whose gradient column is a dump slot).
-Rows carry no state between each other, so they are SORTED BY TYPE: the kernel runs one small counted loop per
-(chunk, type) segment -- no per-row dispatch, loop bodies of a few hundred bytes that live in the L0 instruction cache,
-coefficients from the staged tape with static offsets, row variables (u,w,v) from constant memory.
+Rows carry no state between each other, so they are SORTED BY (type, u, w, v): the kernel runs one small counted loop per
+(chunk, type, u) segment -- no per-row dispatch, x_u and the segment's g_u sum in registers, loop bodies of a few hundred
+bytes that live in the L0 instruction cache, coefficients from the staged tape with static offsets, the row word (w,v)
+from constant memory.  (tools/gen_fat.py goes one step further for the 3B polynomial: rows with the same (w,v) merged.)
 Tape slots per row: [own, a_1..a_n, pad to even] so that every row starts 16-byte aligned.
 """
 import argparse
