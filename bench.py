@@ -201,6 +201,25 @@ def run_ions(args, mb, synth):
     pairs per second.  The CPU baseline is the same call through the oracle driver around the reference's evaluator objects."""
     from mbpol_b200 import mbnrg
     box = synth.make_ion_box(args.nw, args.ions)
+    if args.impl == "reference":        # the reference's own evaluator objects (or the oracle port) on one host core: the
+        from oracle.oracle import Oracle     # reference path is serial per rank (mbnrg.f90:255-337)
+        o = Oracle()
+        for _ in range(args.warmup):
+            o.nrg_forces(box, use_ref=o.have_nrg_reference)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = o.nrg_forces(box, use_ref=o.have_nrg_reference)
+        dt = (time.perf_counter() - t0) / args.steps
+        v = r["nactive"] / dt
+        print(json.dumps({"impl": "reference", "metric": "mbnrg_ion_water_pairs_per_second", "value": v, "unit": "pairs/s", "n_gpus": 1,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "NaCl(aq) MB-nrg 2B: %d H2O + %d Na/Cl" % (box["nw"], box["nions"]),
+                                     "pairs_within_10A": r["npairs"], "pairs_evaluated": r["nactive"], "ion_ion_pairs": r["nionion"]},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 1, "kind": "reference" if o.have_nrg_reference else "port",
+                                           "sample": "the whole step"},
+                          "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     h = mbnrg.mbnrg_init(box["nttm2"], box["ion_code"])
     n = box["mxatms"]
     F = [np.zeros(n) for _ in range(3)]
