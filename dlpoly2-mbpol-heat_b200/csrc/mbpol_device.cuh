@@ -140,6 +140,27 @@ __device__ __forceinline__ void trimer_variables(const double (&r)[27], double* 
     }
 }
 
+// the same without 1/d (recomputed after the polynomial by trimer_rinv: 36 + 27 values less to keep alive across it)
+__device__ __forceinline__ void trimer_x(const double (&r)[27], double* xv)
+{
+#pragma unroll
+    for (int n = 0; n < 36; ++n) {
+        const int a = 3 * V3A[n], b = 3 * V3B[n];
+        const double dx = r[a] - r[b], dy = r[a + 1] - r[b + 1], dz = r[a + 2] - r[b + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        xv[n] = exp(-mbpol_par.k3[V3K[n]] * (d - mbpol_par.d3[V3K[n]]));
+    }
+}
+__device__ __forceinline__ void trimer_rinv(const double (&r)[27], double (&rinv)[36])
+{
+#pragma unroll
+    for (int n = 0; n < 36; ++n) {
+        const int a = 3 * V3A[n], b = 3 * V3B[n];
+        const double dx = r[a] - r[b], dy = r[a + 1] - r[b + 1], dz = r[a + 2] - r[b + 2];
+        rinv[n] = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+}
+
 // switch + chain rule: (x, dEpoly/dx, Epoly) -> E and the per-variable force coefficients cv
 __device__ __forceinline__ void trimer_finish(const double* xv, const double* gp, double Epoly, const double (&rinv)[36], double& E,
                                               double (&cv)[36])
@@ -185,6 +206,24 @@ __device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, do
     }
     trimer_finish(xv, gp, Epoly, rinv, E, cv);
     return true;
+}
+
+// Engines 1 and 3 keep x[36] + g[36] in registers while they walk the tape: instead of spilling the geometry (27 values) and
+// the 36 inverse distances across the polynomial, both are recomputed afterwards (`geom` re-reads the monomers with loads
+// the compiler cannot merge with the first pass).
+template <int ENGINE, class Geom>
+__device__ __forceinline__ void trimer_eval_regeom(Geom geom, double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+{
+    static_assert(ENGINE == 1 || ENGINE == 3, "shared-memory tape engines only");
+    double xv[36], gp[36], Epoly;
+    geom(r, false);
+    trimer_x(r, xv);
+    if (ENGINE == 3) fat_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    else tape_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    double rinv[36];
+    geom(r, true);
+    trimer_rinv(r, rinv);
+    trimer_finish(xv, gp, Epoly, rinv, E, cv);
 }
 
 // gradient on the 9 atoms from cv:  g[3*atom + c]

@@ -325,14 +325,21 @@ __device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, cons
 // K3: trimers.  One thread per accepted trimer of this shard.
 // ---------------------------------------------------------------------------------------------------------
 // imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
+__device__ __forceinline__ double ld_again(const double* p)     // a load the compiler cannot merge with an earlier one
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <bool AGAIN = false>
 __device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict__ mono, const CellInfo& C, int mi, int mj, int mk, double (&r)[27])
 {
     double wj[9], wi[9], wk[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) {
-        wi[c] = mono[(size_t)c * nw + mi];
-        wj[c] = mono[(size_t)c * nw + mj];
-        wk[c] = mono[(size_t)c * nw + mk];
+        wi[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mi) : mono[(size_t)c * nw + mi];
+        wj[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mj) : mono[(size_t)c * nw + mj];
+        wk[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mk) : mono[(size_t)c * nw + mk];
     }
     double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
     double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
@@ -446,9 +453,18 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
         if (valid) bead = mi / O.nwb;
         double r[27];
-        trimer_geometry(nw, mono, C, mi, mj, mk, r);
         double E, cv[36];
-        const bool done = trimer_eval<ENGINE>(r, E, cv, ctx);
+        bool done = true;
+        if constexpr (ENGINE == 1 || ENGINE == 3) {
+            auto geom = [&](double (&rr)[27], bool again) {
+                if (again) trimer_geometry<true>(nw, mono, C, mi, mj, mk, rr);
+                else trimer_geometry<false>(nw, mono, C, mi, mj, mk, rr);
+            };
+            trimer_eval_regeom<ENGINE>(geom, r, E, cv, ctx);
+        } else {
+            trimer_geometry(nw, mono, C, mi, mj, mk, r);
+            done = trimer_eval<ENGINE>(r, E, cv, ctx);
+        }
         const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
         if (done && valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
     }
