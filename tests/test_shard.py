@@ -60,3 +60,42 @@ def test_two_rank_reduction_gloo():
         assert p.exitcode == 0
     for rank, err, _ in res:
         assert err < 1e-12, (rank, err)
+
+
+def _worker_nrg(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mbpol_b200  # noqa: F401
+    from mbpol_b200 import synth
+    from oracle.oracle import Oracle
+    o = Oracle()
+    box = synth.make_ion_box(216, 8)
+    # MB-nrg (row f1): water slices per rank, ion-ion pairs on rank 0 only; forces, energy, virial and stress of the ranks
+    # add up to the single-rank result with ONE all-reduce of the packed partial sums
+    part = o.nrg_forces(box, rank=rank, nranks=world)
+    packed = np.concatenate([part["fxx"], part["fyy"], part["fzz"], [part["eng2"], part["vir2"]], part["stress"]])
+    t = torch.from_numpy(packed)
+    dist.all_reduce(t)
+    full = o.nrg_forces(box)
+    ref = np.concatenate([full["fxx"], full["fyy"], full["fzz"], [full["eng2"], full["vir2"]], full["stress"]])
+    err = float(np.abs(t.numpy() - ref).max() / np.abs(ref).max())
+    q.put((rank, err, part["nionion"], part["npairs"], full["npairs"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_gloo_mbnrg():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker_nrg, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(err < 1e-12 for _, err, _, _, _ in res)
+    assert res[0][2] > 0 and res[1][2] == 0                      # ion-ion pairs live on rank 0
+    assert res[0][3] + res[1][3] == res[0][4]                    # the water slices partition the pair list
