@@ -1,16 +1,14 @@
-// mbpol_device.cuh -- per-cluster device code: geometry -> variables -> polynomial (generated PTX) -> chain rule.
+// mbpol_device.cuh -- per-cluster device code: geometry -> variables -> polynomial (coefficient-tape engines) -> chain rule.
 //
 // B200-native restatement of x2b_v6x_p::operator() (mbpol-2b-poly.cpp:358-682) and x3b_v2x_p::operator()
-// (mbpol-3b-poly.cpp:148-312).  One thread owns one cluster.  The polynomial and its gradient are evaluated by the
-// generated device functions poly{2b,3b}_part<k> (tools/gen_poly.py) through a per-thread record in local memory.
+// (mbpol-3b-poly.cpp:148-312).  One thread owns one cluster.  The polynomial and its gradient are evaluated by one of the
+// coefficient-tape engines: 1 = rows (mbpol_tape.cuh), 3 = fat rows (mbpol_fat.cuh), 4 = symmetry-batched fat rows
+// (mbpol_sym.cuh, 3B only).
 #pragma once
 #include <cuda_runtime.h>
-#include "gen/poly_gen.h"
 #include "mbpol_tape.cuh"
 #include "mbpol_fat.cuh"
-
-// linear coefficients: referenced by name from the generated PTX (.extern .const)
-extern __constant__ double mbpol_cwin[];   // the single constant-bank window: PTX-engine coefficient tables or one tape window
+#include "mbpol_sym.cuh"
 
 struct MbpolParams {   // non-linear parameters, mbpol-2b-poly.cpp:1846-1866, mbpol-3b-poly.cpp:1486-1503
     double k2[8];       // HH_intra, OH_intra, HH_coul, OH_coul, OO_coul, XH, XO, XX
@@ -78,43 +76,12 @@ __device__ __forceinline__ double switch_fn(double r, double ri, double rf, doub
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// polynomial front-ends.  ENGINE 0: generated straight-line PTX parts (tools/gen_poly.py), per-thread record in
-// local memory.  ENGINE 1: coefficient-tape interpreter (tools/gen_tape.py, mbpol_tape.cuh); needs the whole CTA.
+// polynomial front-ends: every engine walks a coefficient tape staged in shared memory and needs the whole CTA
 // ---------------------------------------------------------------------------------------------------------
 struct PolyCtx {
-    void* smem;              // TapeSmem<NV>* (ENGINE 1) / TapeCSmem<NV>* (ENGINE 2)
-    const double* tape;      // device tape for ENGINE 1
-    // ENGINE 2 (constant-window passes): partial (g, E) of cluster `idx` of `count` lives in gbuf[c * count + idx]
-    double* gbuf;
-    long long idx, count;
-    bool first, last, valid;
+    void* smem;              // the engine's dynamic shared memory (TapeSmem<NV> / SymSmem)
+    const double* tape;      // device coefficient tape of the engine
 };
-
-// engine 2 row loops: separate ptxas units (mbpol_tape_cpass.cu)
-extern "C" __device__ void mbpol_tape3b_cpass(double* rec, TapeCSmem<36>* sm);
-extern "C" __device__ void mbpol_tape2b_cpass(double* rec, TapeCSmem<31>* sm);
-
-// one constant-window pass on a record [x(NV) | E | g(NV)]; returns true when the polynomial is complete
-template <int NV>
-__device__ __forceinline__ bool cpass_step(double* rec, const PolyCtx& ctx)
-{
-    if (ctx.first) {
-#pragma unroll
-        for (int c = NV; c < 2 * NV + 1; ++c) rec[c] = 0.0;
-    } else {
-#pragma unroll
-        for (int c = 0; c < NV; ++c) rec[NV + 1 + c] = ctx.gbuf[(size_t)c * ctx.count + ctx.idx];
-        rec[NV] = ctx.gbuf[(size_t)NV * ctx.count + ctx.idx];
-    }
-    if (NV == 36) mbpol_tape3b_cpass(rec, reinterpret_cast<TapeCSmem<36>*>(ctx.smem));
-    else mbpol_tape2b_cpass(rec, reinterpret_cast<TapeCSmem<31>*>(ctx.smem));
-    if (!ctx.last && ctx.valid) {
-#pragma unroll
-        for (int c = 0; c < NV; ++c) ctx.gbuf[(size_t)c * ctx.count + ctx.idx] = rec[NV + 1 + c];
-        ctx.gbuf[(size_t)NV * ctx.count + ctx.idx] = rec[NV];
-    }
-    return ctx.last;
-}
 
 // =========================================================================================================
 // 3B
@@ -181,45 +148,35 @@ __device__ __forceinline__ void trimer_finish(const double* xv, const double* gp
     E = s * Epoly;
 }
 
-// returns false when the polynomial is not complete yet (engine 2, not the last pass): E and cv are then undefined
+// polynomial of one trimer with the engine's tape walk (all threads of the CTA must call it)
 template <int ENGINE>
-__device__ __forceinline__ bool trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+__device__ __forceinline__ void poly3b_eval(double (&xv)[36], double (&gp)[36], double& Epoly, const PolyCtx& ctx)
 {
-    constexpr bool SMEM_TAPE = ENGINE == 1 || ENGINE == 3;     // engines that walk a shared-memory tape: x[], g[] in registers
-    double xv[SMEM_TAPE ? 36 : POLY3B_RECORD_DOUBLES], gp_[SMEM_TAPE ? 36 : 1];
-    double* gp = SMEM_TAPE ? gp_ : xv + 37;      // ENGINE 0/2: x and g live in the per-thread record (local memory)
-    double rinv[36];
-    trimer_variables(r, xv, rinv);
-    double Epoly;
-    if (ENGINE == 0) {
-        POLY3B_CALL_ALL(xv, 1u);
-        Epoly = xv[36];
-    } else if (ENGINE == 2) {
-        if (!cpass_step<36>(xv, ctx)) return false;
-        Epoly = xv[36];
-    } else if (ENGINE == 3) {
-        fat_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
-                     *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
-    } else {
-        tape_eval<3, 36>(ctx.tape, reinterpret_cast<double(&)[36]>(xv), reinterpret_cast<double(&)[36]>(gp_), Epoly,
-                         *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
-    }
-    trimer_finish(xv, gp, Epoly, rinv, E, cv);
-    return true;
+    static_assert(ENGINE == 1 || ENGINE == 3 || ENGINE == 4, "unknown polynomial engine");
+    if constexpr (ENGINE == 4) sym_eval3b(ctx.tape, xv, gp, Epoly, *reinterpret_cast<SymSmem*>(ctx.smem));
+    else if constexpr (ENGINE == 3) fat_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    else tape_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
 }
 
-// Engines 1 and 3 keep x[36] + g[36] in registers while they walk the tape: instead of spilling the geometry (27 values) and
+template <int ENGINE>
+__device__ __forceinline__ void trimer_eval(const double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
+{
+    double xv[36], gp[36], rinv[36], Epoly;
+    trimer_variables(r, xv, rinv);
+    poly3b_eval<ENGINE>(xv, gp, Epoly, ctx);
+    trimer_finish(xv, gp, Epoly, rinv, E, cv);
+}
+
+// The engines keep x[36] + g[36] in registers while they walk the tape: instead of spilling the geometry (27 values) and
 // the 36 inverse distances across the polynomial, both are recomputed afterwards (`geom` re-reads the monomers with loads
 // the compiler cannot merge with the first pass).
 template <int ENGINE, class Geom>
 __device__ __forceinline__ void trimer_eval_regeom(Geom geom, double (&r)[27], double& E, double (&cv)[36], const PolyCtx& ctx)
 {
-    static_assert(ENGINE == 1 || ENGINE == 3, "shared-memory tape engines only");
     double xv[36], gp[36], Epoly;
     geom(r, false);
     trimer_x(r, xv);
-    if (ENGINE == 3) fat_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
-    else tape_eval<3, 36>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<36>*>(ctx.smem));
+    poly3b_eval<ENGINE>(xv, gp, Epoly, ctx);
     double rinv[36];
     geom(r, true);
     trimer_rinv(r, rinv);
@@ -304,14 +261,11 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
     for (int i = 0; i < 18; ++i) g[i] = 0.0;
     if (fm)
         for (int i = 0; i < 108; ++i) fm[i] = 0.0;
-    const bool inside = !(rOO > mbpol_par.r2f);
-    constexpr bool SMEM_TAPE = ENGINE == 1 || ENGINE == 3;     // engines that walk a shared-memory tape with CTA barriers
-    if (!SMEM_TAPE && !inside && (ENGINE == 0 || ctx.last)) return false;   // those have CTA barriers: every thread walks on
+    const bool inside = !(rOO > mbpol_par.r2f);     // the tape walk has CTA barriers: every thread walks on regardless
     lonepair_sites(xc + 0, xc + 18, xc + 21);
     lonepair_sites(xc + 9, xc + 24, xc + 27);
 
-    double xv[SMEM_TAPE ? 31 : POLY2B_RECORD_DOUBLES], gp_[SMEM_TAPE ? 31 : 1];
-    double* gp = SMEM_TAPE ? gp_ : xv + 32;
+    double xv[31], gp[31];
     double gfac[31];    // dv/dr / r : the variable's gradient is gfac * (r_a - r_b)
 #pragma unroll
     for (int n = 0; n < 31; ++n) {
@@ -332,19 +286,9 @@ __device__ __noinline__ bool dimer_eval(const double* w, double& E, double* g, d
         }
     }
     double Epoly;
-    if (ENGINE == 0) {
-        POLY2B_CALL_ALL(xv, 1u);
-        Epoly = xv[31];
-    } else if (ENGINE == 2) {
-        if (!cpass_step<31>(xv, ctx)) return false;
-        Epoly = xv[31];
-    } else if (ENGINE == 3) {
-        fat_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,
-                        *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
-    } else {
-        tape_eval<2, 31>(ctx.tape, reinterpret_cast<double(&)[31]>(xv), reinterpret_cast<double(&)[31]>(gp_), Epoly,
-                         *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
-    }
+    static_assert(ENGINE == 1 || ENGINE == 3, "unknown polynomial engine");
+    if constexpr (ENGINE == 3) fat_eval<2, 31>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
+    else tape_eval<2, 31>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
     if (!inside) return false;
 
     double xg[30];

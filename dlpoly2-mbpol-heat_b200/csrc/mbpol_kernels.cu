@@ -22,13 +22,10 @@
 #include <vector>
 
 #include "mbpol_b200.h"
-#include "mbpol_device.cuh"
+#include "mbpol_cluster.cuh"
 #include "gen/mbpol_model_data.h"
 #include <cstdlib>
 
-__constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];   // PTX-engine coefficient tables [2B | 3B] or one constant-tape window
-__constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
-__constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
 __constant__ MbpolParams mbpol_par;
 __constant__ unsigned c_tape_rowvars2b[TAPE2B_NROWS];
 __constant__ unsigned c_tape_rowvars3b[TAPE3B_NROWS];
@@ -42,19 +39,27 @@ __constant__ unsigned c_fat_segs2b[FAT2B_NSEGS];
 __constant__ unsigned c_fat_segs3b[FAT3B_NSEGS];
 __constant__ int c_fat_chunks2b[FAT2B_NCHUNKS + 1][3];
 __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
+__constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
+__constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
+__constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
+
+using namespace mbpol_k;
+
+// the (kernel, engine) instantiations live in mbpol_inst.cu
+namespace mbpol_k {
+extern template __global__ void k_dimers<1>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_dimers<3>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_trimers<1>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_trimers<3>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_trimers<4>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_eval_dimers<1>(int, const double*, double*, double*, double*, const double*);
+extern template __global__ void k_eval_dimers<3>(int, const double*, double*, double*, double*, const double*);
+extern template __global__ void k_eval_trimers<1>(int, const double*, double*, double*, double*, const double*);
+extern template __global__ void k_eval_trimers<3>(int, const double*, double*, double*, double*, const double*);
+extern template __global__ void k_eval_trimers<4>(int, const double*, double*, double*, double*, const double*);
+}
 
 namespace {
-
-constexpr int NB2_CAP = 96;    // neighbours j>i within r2f (6.5 A): ~19 on average in liquid water
-constexpr int NB3_CAP = 40;    // neighbours within r3f (4.5 A): ~13 on average
-constexpr int NSCAL = 32;
-enum { S_ENG2 = 0, S_VIR2 = 1, S_ENG3 = 2, S_VIR3 = 3, S_STRESS = 4, S_JFLUX = 13, S_ND = 22, S_NT = 23 };
-
-struct OutPtrs {      // views into the packed output buffer
-    double *fx, *fy, *fz, *aeng, *astress, *afd, *scal;
-    int mxatms;       // all beads: nbeads * mxb
-    int nwb, mxb;     // waters / atoms per bead (bead-batched calls; one bead otherwise); scalars of bead b at scal + b*NSCAL
-};
 
 // ---------------------------------------------------------------------------------------------------------
 // K0: gather + image_monomers.  mono[c*nw + m], c = 0..8 (O xyz, H1 xyz, H2 xyz)
@@ -260,317 +265,6 @@ __global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// block reduction of NV per-thread doubles -> atomicAdd into dst[0..NV)
-// ---------------------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_reduce_add(double (&v)[NV], double* dst)
-{
-    __shared__ double red[NV][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double x = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) red[k][warp] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double x = lane < nwarp ? red[k][lane] : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-            if (lane == 0) atomicAdd(dst + k, x);
-        }
-    }
-}
-
-// scalars are kept per bead: reduce over the block when all its clusters belong to one bead (always, except at the
-// few blocks that straddle a bead boundary of a bead-batched call), else one atomic per thread
-template <int NV>
-__device__ __forceinline__ void block_reduce_add_bead(double (&v)[NV], double* scal, int slot, int bead /* < 0: idle lane */)
-{
-    __shared__ int bead0;
-    if (threadIdx.x == 0) bead0 = bead;          // thread 0 of a launched block always owns a cluster
-    __syncthreads();
-    const int b0 = bead0;
-    if (__syncthreads_and(bead < 0 || bead == b0)) {
-        block_reduce_add<NV>(v, scal + (size_t)b0 * NSCAL + slot);
-    } else if (bead >= 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) atomicAdd(scal + (size_t)bead * NSCAL + slot + k, v[k]);
-    }
-    __syncthreads();
-}
-
-// per-atom 3x3 tensors are stored bead-major, [nbeads][9][mxb]: component q of (0-based, all-bead) atom `atom` sits at
-// base + tensor_base(atom) + mxb*q -- for one bead this is the Fortran layout atomic_stress(mxatms,3,3)
-__device__ __forceinline__ size_t tensor_base(const OutPtrs& O, int atom) { return (size_t)atom + (size_t)(atom / O.mxb) * 8 * O.mxb; }
-
-// per-atom force-decomposition tensor W (heatcurrent.f90:529-533, 703-728):
-//   W_i(a,b) += (n*x_i - sum_j x_j)_a^raw * f_b ,  f = -g_i*engunit/n
-__device__ __forceinline__ void scatter_fdecomp(const OutPtrs& O, int atom, const double* xraw_i, const double* xsum, int n,
-                                                const double* f)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double ra = n * xraw_i[a] - xsum[a];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) atomicAdd(O.afd + tensor_base(O, atom) + (size_t)O.mxb * (a + 3 * b), ra * f[b]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// K3: trimers.  One thread per accepted trimer of this shard.
-// ---------------------------------------------------------------------------------------------------------
-// imaging exactly as do_trimer (mbpol.f90:843-882): waters i and k next to water j; origin moved to O_j
-__device__ __forceinline__ double ld_again(const double* p)     // a load the compiler cannot merge with an earlier one
-{
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-template <bool AGAIN = false>
-__device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict__ mono, const CellInfo& C, int mi, int mj, int mk, double (&r)[27])
-{
-    double wj[9], wi[9], wk[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-        wi[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mi) : mono[(size_t)c * nw + mi];
-        wj[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mj) : mono[(size_t)c * nw + mj];
-        wk[c] = AGAIN ? ld_again(mono + (size_t)c * nw + mk) : mono[(size_t)c * nw + mk];
-    }
-    double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
-    double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
-    image_vec(C, a0, a1, a2);
-    image_vec(C, b0, b1, b2);
-    const double ra[3] = {a0, a1, a2}, rb[3] = {b0, b1, b2};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        r[c] = ra[c];                               // O_i' - O_j
-        r[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
-        r[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
-        r[9 + c] = 0.0;
-        r[12 + c] = wj[3 + c] - wj[c];
-        r[15 + c] = wj[6 + c] - wj[c];
-        r[18 + c] = -rb[c];                         // O_k' - O_j
-        r[21 + c] = (wk[3 + c] - wk[c]) - rb[c];
-        r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
-    }
-}
-
-// accumulation of one evaluated trimer (mbpol.f90:896-1267): forces, per-atom energy, W, S; returns the block scalars
-__device__ __forceinline__ void trimer_scatter(const double (&r)[27], double E, const double (&cv)[36], const int (&o)[3],
-                                               const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
-                                               const OutPtrs& O, int flags, double (&sc)[8])
-{
-    double g[27];
-    trimer_gradient(r, cv, g);
-    const double eu = MBPOL_ENGUNIT;
-    sc[0] = E * eu;
-#pragma unroll
-    for (int a = 0; a < 9; ++a) {
-        const int atom = o[a / 3] - 1 + (a % 3);
-        const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
-        atomicAdd(O.fx + atom, -gx);
-        atomicAdd(O.fy + atom, -gy);
-        atomicAdd(O.fz + atom, -gz);
-        sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
-        sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
-        sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
-    }
-    if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
-        const double e9 = (1.0 / 9.0) * E * eu;
-#pragma unroll
-        for (int a = 0; a < 9; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e9);
-    }
-    if (flags & MBPOL_B200_WANT_FDECOMP) {
-        double xs[3] = {0, 0, 0}, xraw[27];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const int atom = o[a / 3] - 1 + (a % 3);
-            xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
-            xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
-        }
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const double f[3] = {-(1.0 / 9.0) * g[3 * a] * eu, -(1.0 / 9.0) * g[3 * a + 1] * eu, -(1.0 / 9.0) * g[3 * a + 2] * eu};
-            scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 9, f);
-        }
-    }
-    if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {
-        // S_i(a,b) = 1/2*eu*sum_{j != i} (r_i-r_j)_a FM[i][j]_b with FM[i][j] = cv_n (r_i - r_j): a symmetric
-        // tensor cv_n d (x) d that goes to BOTH atoms of variable n (mbpol.f90:945-966)
-        double S[9][6];
-#pragma unroll
-        for (int a = 0; a < 9; ++a)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) S[a][q] = 0.0;
-#pragma unroll
-        for (int n = 0; n < 36; ++n) {
-            const int a = V3A[n], b = V3B[n];
-            const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
-            const double h = 0.5 * eu * cv[n];
-            const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
-        }
-        const size_t n = O.mxb;
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            double* p = O.astress + tensor_base(O, o[a / 3] - 1 + (a % 3));
-            atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
-            atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
-            atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
-        }
-    }
-}
-
-__device__ __forceinline__ void trimer_block_scalars(double (&sc)[8], const OutPtrs& O, int bead)
-{
-    double v2[2] = {sc[0], sc[1]};
-    block_reduce_add_bead<2>(v2, O.scal, S_ENG3, bead);
-    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
-    block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
-}
-
-template <int ENGINE>
-__global__ void __launch_bounds__(256, 1)
-k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-          const double* __restrict__ tape, double* __restrict__ gbuf, bool first, bool last)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t0_ < ntri;
-    // idle lanes shadow the last trimer: engine 1 has CTA barriers, engine 2 needs thread-independent control flow
-    const long long t = valid ? t0_ : ntri - 1;
-    const PolyCtx ctx{dyn_smem, tape, gbuf, t, ntri, first, last, valid};
-    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
-    int bead = -1;
-    if (ENGINE != 0 || valid) {
-        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
-        if (valid) bead = mi / O.nwb;
-        double r[27];
-        double E, cv[36];
-        bool done = true;
-        if constexpr (ENGINE == 1 || ENGINE == 3) {
-            auto geom = [&](double (&rr)[27], bool again) {
-                if (again) trimer_geometry<true>(nw, mono, C, mi, mj, mk, rr);
-                else trimer_geometry<false>(nw, mono, C, mi, mj, mk, rr);
-            };
-            trimer_eval_regeom<ENGINE>(geom, r, E, cv, ctx);
-        } else {
-            trimer_geometry(nw, mono, C, mi, mj, mk, r);
-            done = trimer_eval<ENGINE>(r, E, cv, ctx);
-        }
-        const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
-        if (done && valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
-    }
-    if (ENGINE != 2 || last) trimer_block_scalars(sc, O, bead);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// K2: dimers
-// ---------------------------------------------------------------------------------------------------------
-template <int ENGINE>
-__global__ void __launch_bounds__(256, 1)
-k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-         const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-         const double* __restrict__ tape, double* __restrict__ gbuf, bool first, bool last)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t0_ < ndim;
-    const long long t = valid ? t0_ : ndim - 1;
-    const PolyCtx ctx{dyn_smem, tape, gbuf, t, ndim, first, last, valid};
-    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int bead = -1;
-    if (ENGINE != 0 || valid) {
-        const int mi = dim[t].x, mj = dim[t].y;
-        if (valid) bead = mi / O.nwb;
-        double wi[9], wj[9], w[18];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            wi[c] = mono[(size_t)c * nw + mi];
-            wj[c] = mono[(size_t)c * nw + mj];
-        }
-        double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
-        image_vec(C, a0, a1, a2);                       // do_dimer, mbpol.f90:496-509; origin moved to O_j
-        const double ra[3] = {a0, a1, a2};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            w[c] = ra[c];
-            w[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
-            w[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
-            w[9 + c] = 0.0;
-            w[12 + c] = wj[3 + c] - wj[c];
-            w[15 + c] = wj[6 + c] - wj[c];
-        }
-        double E, g[18];
-        double fm[108];
-        const bool want_s = (flags & MBPOL_B200_WANT_ATOMIC_STRESS) != 0;
-        const bool done = dimer_eval<ENGINE>(w, E, g, want_s ? fm : nullptr, ctx) || ENGINE != 2;
-        const double eu = MBPOL_ENGUNIT;
-        const int o[2] = {list[3 * mi], list[3 * mj]};
-        if (valid && done && (ENGINE != 2 || last)) {
-        sc[0] = E * eu;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const int atom = o[a / 3] - 1 + (a % 3);
-            const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
-            atomicAdd(O.fx + atom, -gx);
-            atomicAdd(O.fy + atom, -gy);
-            atomicAdd(O.fz + atom, -gz);
-            sc[1] += w[3 * a] * gx + w[3 * a + 1] * gy + w[3 * a + 2] * gz;
-            sc[2] -= w[3 * a] * gx; sc[3] -= w[3 * a] * gy; sc[4] -= w[3 * a] * gz;
-            sc[5] -= w[3 * a + 1] * gy; sc[6] -= w[3 * a + 1] * gz; sc[7] -= w[3 * a + 2] * gz;
-        }
-        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
-            const double e6 = (1.0 / 6.0) * E * eu;
-#pragma unroll
-            for (int a = 0; a < 6; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e6);
-        }
-        if (flags & MBPOL_B200_WANT_FDECOMP) {
-            double xs[3] = {0, 0, 0}, xraw[18];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const int atom = o[a / 3] - 1 + (a % 3);
-                xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
-                xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
-            }
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const double f[3] = {-(1.0 / 6.0) * g[3 * a] * eu, -(1.0 / 6.0) * g[3 * a + 1] * eu, -(1.0 / 6.0) * g[3 * a + 2] * eu};
-                scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 6, f);
-            }
-        }
-        if (want_s) {   // mbpol.f90:558-579: S_i(a,b) = 1/2*eu*sum_{j != i} (r_i - r_j)_a * FM[i][j]_b  (FM is NOT antisymmetric)
-            const size_t n = O.mxb;
-            for (int i = 0; i < 6; ++i) {
-                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                for (int j = 0; j < 6; ++j) {
-                    if (i == j) continue;
-                    for (int a = 0; a < 3; ++a) {
-                        const double ra_ = w[3 * i + a] - w[3 * j + a];
-                        for (int b = 0; b < 3; ++b) S[a + 3 * b] += ra_ * fm[18 * i + 3 * j + b];
-                    }
-                }
-                double* p = O.astress + tensor_base(O, o[i / 3] - 1 + (i % 3));
-                for (int q = 0; q < 9; ++q) atomicAdd(p + n * q, 0.5 * eu * S[q]);
-            }
-        }
-        }   // valid
-    }
-    if (ENGINE == 2 && !last) return;
-    double v2[2] = {sc[0], sc[1]};
-    block_reduce_add_bead<2>(v2, O.scal, S_ENG2, bead);
-    double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
-    block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // K5: heat-flux contractions over the atoms of THIS shard's partial sums (linear, so partials add up)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_flux(OutPtrs O, const double* __restrict__ vx, const double* __restrict__ vy,
@@ -605,60 +299,6 @@ __global__ void k_flux(OutPtrs O, const double* __restrict__ vx, const double* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// batched per-cluster kernels (legacy ABI / KAT tests)
-// ---------------------------------------------------------------------------------------------------------
-template <int ENGINE>
-__global__ void __launch_bounds__(256, 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape, nullptr, 0, 0, true, true, true};
-    const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ENGINE == 0 && t0_ >= n) return;
-    const int t = min(t0_, n - 1);
-    double ww[18], gg[18], e, f[108];
-    for (int i = 0; i < 18; ++i) ww[i] = w[(size_t)18 * t + i];
-    dimer_eval<ENGINE>(ww, e, gg, fm ? f : nullptr, ctx);
-    if (t0_ >= n) return;
-    E[t] = e;
-    for (int i = 0; i < 18; ++i) g[(size_t)18 * t + i] = gg[i];
-    if (fm)
-        for (int i = 0; i < 108; ++i) fm[(size_t)108 * t + i] = f[i];
-}
-
-template <int ENGINE>
-__global__ void __launch_bounds__(256, 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
-{
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const PolyCtx ctx{dyn_smem, tape, nullptr, 0, 0, true, true, true};
-    const int t0_ = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ENGINE == 0 && t0_ >= n) return;
-    const int t = min(t0_, n - 1);
-    double r[27], cv[36], gg[27], e;
-#pragma unroll
-    for (int i = 0; i < 27; ++i) r[i] = w[(size_t)27 * t + i];
-    trimer_eval<ENGINE>(r, e, cv, ctx);
-    if (t0_ >= n) return;
-    trimer_gradient(r, cv, gg);
-    E[t] = e;
-#pragma unroll
-    for (int i = 0; i < 27; ++i) g[(size_t)27 * t + i] = gg[i];
-    if (fm) {
-        double* f = fm + (size_t)243 * t;
-        for (int i = 0; i < 243; ++i) f[i] = 0.0;
-#pragma unroll
-        for (int n_ = 0; n_ < 36; ++n_) {
-            const int a = V3A[n_], b = V3B[n_];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double d = cv[n_] * (r[3 * a + c] - r[3 * b + c]);
-                f[27 * a + 3 * b + c] = d;
-                f[27 * b + 3 * a + c] = -d;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // FP64 roofline probe: 8 independent register-resident DFMA chains per thread (the denominator bench.py quotes)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b)
@@ -682,59 +322,37 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 // host side
 // =========================================================================================================
 std::once_flag g_const_once[16];
-double* g_tape2b[16] = {nullptr};
+double* g_tape2b[16] = {nullptr};     // engine 1: coefficients in row order
 double* g_tape3b[16] = {nullptr};
 double* g_fat3b[16] = {nullptr};      // engine 3: the coefficients in fat-row order
 double* g_fat2b[16] = {nullptr};
-double* g_coefwin[16] = {nullptr};
+double* g_sym3b[16] = {nullptr};      // engine 4: the coefficients of the super rows, weighted |orbit| / |K|
 
-// (re)fill the constant-bank window, ordered on `s` behind the kernels that read the previous content
-cudaError_t load_window(const double* dsrc, size_t ndoubles, cudaStream_t s)
-{
-    return cudaMemcpyToSymbolAsync(mbpol_cwin, dsrc, ndoubles * 8, 0, cudaMemcpyDeviceToDevice, s);
-}
-// engine 2: window = [TapeCPassHeader (16 B) | tape slots of pass p]
-TapeCPassHeader* g_hdr2b[16] = {nullptr};
-TapeCPassHeader* g_hdr3b[16] = {nullptr};
-cudaError_t load_pass_window(int device, int which, int p, cudaStream_t s)
-{
-    const int(*tab)[3] = which == 3 ? TAPE3B_CPASS_HOST : TAPE2B_CPASS_HOST;
-    const TapeCPassHeader* hdr = (which == 3 ? g_hdr3b : g_hdr2b)[device] + p;
-    const double* tape = (which == 3 ? g_tape3b : g_tape2b)[device] + tab[p][2];
-    cudaError_t e = cudaMemcpyToSymbolAsync(mbpol_cwin, hdr, sizeof(TapeCPassHeader), 0, cudaMemcpyDeviceToDevice, s);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbolAsync(mbpol_cwin, tape, (size_t)(tab[p + 1][2] - tab[p][2]) * 8, 16, cudaMemcpyDeviceToDevice, s);
-}
-cudaError_t load_coef_window(int device, cudaStream_t s) { return load_window(g_coefwin[device], MBPOL_NCOEF2B + MBPOL_NCOEF3B, s); }
-
-// polynomial engine: 0 = straight-line PTX parts, 1 = coefficient tape staged in shared memory (rows), 2 = coefficient tape in
-// the constant bank (3B in NCPASS launches; 2B uses engine 1), 3 = shared-memory tape with FAT rows.
-// MBPOL_B200_ENGINE=ptx|tape|ctape|fat overrides the default.
+// polynomial engine: 1 = coefficient tape staged in shared memory (rows), 3 = the same with FAT rows, 4 = fat rows batched
+// over molecule permutations (3B only).  MBPOL_B200_ENGINE=tape|fat|sym overrides the 3B default, MBPOL_B200_ENGINE_2B=tape|fat
+// the 2B one.
 #ifndef MBPOL_DEFAULT_ENGINE
-#define MBPOL_DEFAULT_ENGINE 3
+#define MBPOL_DEFAULT_ENGINE 4
 #endif
 int default_engine()
 {
     const char* e = std::getenv("MBPOL_B200_ENGINE");
-    if (e && std::string(e) == "ptx") return 0;
     if (e && std::string(e) == "tape") return 1;
-    if (e && std::string(e) == "ctape") return 2;
     if (e && std::string(e) == "fat") return 3;
+    if (e && std::string(e) == "sym") return 4;
     return MBPOL_DEFAULT_ENGINE;
 }
-// the 2B polynomial may use another engine than the 3B one (MBPOL_B200_ENGINE_2B=ptx|tape|fat; ctape falls back to tape)
 #ifndef MBPOL_DEFAULT_ENGINE_2B
 #define MBPOL_DEFAULT_ENGINE_2B 1   /* measured: rows 3.6-3.8 ms, fat rows 4.05 ms for the 2B polynomial (521 fat rows of 27 shapes merge only 2 rows each) */
 #endif
-int default_engine_2b(int engine3b)
+int default_engine_2b()
 {
     const char* e = std::getenv("MBPOL_B200_ENGINE_2B");
-    if (e && std::string(e) == "ptx") return 0;
     if (e && std::string(e) == "tape") return 1;
     if (e && std::string(e) == "fat") return 3;
-    return std::getenv("MBPOL_B200_ENGINE") ? engine3b : MBPOL_DEFAULT_ENGINE_2B;
+    return MBPOL_DEFAULT_ENGINE_2B;
 }
-constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>), SMEM2C = sizeof(TapeCSmem<31>), SMEM3C = sizeof(TapeCSmem<36>);
+constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>);
 
 template <class K>
 cudaError_t allow_smem(K kernel, size_t bytes)
@@ -805,27 +423,17 @@ int upload_constants(int device)
         if (cudaMemcpyToSymbol(c_fat_rowvars3b, FAT3B_ROWVARS_HOST, sizeof(FAT3B_ROWVARS_HOST)) != cudaSuccess) return 1;
         if (cudaMemcpyToSymbol(c_fat_segs3b, FAT3B_SEGS_HOST, sizeof(FAT3B_SEGS_HOST)) != cudaSuccess) return 1;
         if (cudaMemcpyToSymbol(c_fat_chunks3b, FAT3B_CHUNKS_HOST, sizeof(FAT3B_CHUNKS_HOST)) != cudaSuccess) return 1;
-        std::vector<TapeCPassHeader> h2(TAPE2B_NCPASS), h3(TAPE3B_NCPASS);
-        for (int p = 0; p < TAPE2B_NCPASS; ++p)
-            h2[p] = {TAPE2B_CPASS_HOST[p][0], TAPE2B_CPASS_HOST[p + 1][0], (unsigned)TAPE2B_CPASS_HOST[p][1], (unsigned)TAPE2B_CPASS_HOST[p + 1][1] - 1u};
-        for (int p = 0; p < TAPE3B_NCPASS; ++p)
-            h3[p] = {TAPE3B_CPASS_HOST[p][0], TAPE3B_CPASS_HOST[p + 1][0], (unsigned)TAPE3B_CPASS_HOST[p][1], (unsigned)TAPE3B_CPASS_HOST[p + 1][1] - 1u};
-        if (cudaMalloc(&g_hdr2b[device], h2.size() * sizeof(TapeCPassHeader)) != cudaSuccess || cudaMalloc(&g_hdr3b[device], h3.size() * sizeof(TapeCPassHeader)) != cudaSuccess) return 1;
-        if (cudaMemcpy(g_hdr2b[device], h2.data(), h2.size() * sizeof(TapeCPassHeader), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
-        if (cudaMemcpy(g_hdr3b[device], h3.data(), h3.size() * sizeof(TapeCPassHeader), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        std::vector<double> ts(SYM3B_NTAPE);                // engine 4: value = a * |orbit| / |K|
+        for (int i = 0; i < SYM3B_NTAPE; ++i)
+            ts[i] = SYM3B_COEFIDX_HOST[i] < 0 ? 0.0 : MBPOL_COEF3B_HOST[SYM3B_COEFIDX_HOST[i]] * (double)SYM3B_COEFNUM_HOST[i] / (double)SYM3B_K;
+        double* ds = nullptr;
+        if (cudaMalloc(&ds, ts.size() * 8) != cudaSuccess || cudaMemcpy(ds, ts.data(), ts.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+        g_sym3b[device] = ds;
+        if (cudaMemcpyToSymbol(c_sym_rowvars3b, SYM3B_ROWVARS_HOST, sizeof(SYM3B_ROWVARS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_sym_segs3b, SYM3B_SEGS_HOST, sizeof(SYM3B_SEGS_HOST)) != cudaSuccess) return 1;
+        if (cudaMemcpyToSymbol(c_sym_chunks3b, SYM3B_CHUNKS_HOST, sizeof(SYM3B_CHUNKS_HOST)) != cudaSuccess) return 1;
     }
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(c_tape_csegs2b, TAPE2B_CSEGS_HOST, sizeof(TAPE2B_CSEGS_HOST)) != cudaSuccess) return 1;
-    if (cudaMemcpyToSymbol(c_tape_csegs3b, TAPE3B_CSEGS_HOST, sizeof(TAPE3B_CSEGS_HOST)) != cudaSuccess) return 1;
-    {   // PTX engine: both coefficient tables as one device image of the constant window
-        std::vector<double> w(MBPOL_NCOEF2B + MBPOL_NCOEF3B);
-        std::copy(MBPOL_COEF2B_HOST, MBPOL_COEF2B_HOST + MBPOL_NCOEF2B, w.begin());
-        std::copy(MBPOL_COEF3B_HOST, MBPOL_COEF3B_HOST + MBPOL_NCOEF3B, w.begin() + MBPOL_NCOEF2B);
-        double* d = nullptr;
-        if (cudaMalloc(&d, w.size() * 8) != cudaSuccess) return 1;
-        if (cudaMemcpy(d, w.data(), w.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
-        g_coefwin[device] = d;
-    }
     return 0;
 }
 
@@ -867,7 +475,7 @@ struct mbpol_b200_handle {
     CellInfo C;
     Grid G;
     int ncells = 0;
-    DevBuf<double> xyz, vel, mono, out, gbuf;
+    DevBuf<double> xyz, vel, mono, out;
     DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag;
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll;
@@ -935,9 +543,9 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     if (cudaSetDevice(device) != cudaSuccess) return MBPOL_B200_ECUDA;
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
-    h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine(); h->engine2b = default_engine_2b(h->engine);
-    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_dimers<3>, SMEM2B) != cudaSuccess ||
-        allow_smem(k_dimers<2>, SMEM2C) != cudaSuccess || allow_smem(k_trimers<2>, SMEM3C) != cudaSuccess) {
+    h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine(); h->engine2b = default_engine_2b();
+    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_dimers<3>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
+        allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<4>, SMEM3B) != cudaSuccess) {
         delete h;
         return MBPOL_B200_ECUDA;
     }
@@ -1105,48 +713,24 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     OutPtrs O = h->views();
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     if (h->nd_shard > 0) {
-        const unsigned gd = (unsigned)((h->nd_shard + 255) / 256);
+        const unsigned gd = (unsigned)((h->nd_shard + TAPE_BS - 1) / TAPE_BS);
         const int2* dl = h->dimers.p + d0;
-        if (h->engine2b == 2) {
-            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * std::max(h->nt_shard, h->nd_shard)));
-            for (int p = 0; p < TAPE2B_NCPASS; ++p) {
-                CUDA_TRY(h, load_pass_window(h->device, 2, p, s));
-                k_dimers<2><<<gd, 256, SMEM2C, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, h->gbuf.p,
-                                                    p == 0, p == TAPE2B_NCPASS - 1);
-                ++h->launches;
-            }
-            --h->launches;
-        } else if (h->engine2b == 3) {
-            k_dimers<3><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device], nullptr, true, true);
-        } else if (h->engine2b == 1) {
-            k_dimers<1><<<gd, 256, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device], nullptr, true, true);
-        } else {
-            CUDA_TRY(h, load_coef_window(h->device, s));
-            k_dimers<0><<<gd, 256, 0, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, nullptr, true, true);
-        }
+        if (h->engine2b == 3)
+            k_dimers<3><<<gd, TAPE_BS, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
+        else
+            k_dimers<1><<<gd, TAPE_BS, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     if (h->nt_shard > 0) {
-        const unsigned gt = (unsigned)((h->nt_shard + 255) / 256);
+        const unsigned gt = (unsigned)((h->nt_shard + TAPE_BS - 1) / TAPE_BS);
         const int* tl = h->trimers.p + 3 * t0;
-        if (h->engine == 2) {
-            CUDA_TRY(h, h->gbuf.reserve((size_t)37 * std::max(h->nt_shard, h->nd_shard)));
-            for (int p = 0; p < TAPE3B_NCPASS; ++p) {
-                CUDA_TRY(h, load_pass_window(h->device, 3, p, s));
-                k_trimers<2><<<gt, 256, SMEM3C, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, h->gbuf.p,
-                                                     p == 0, p == TAPE3B_NCPASS - 1);
-                ++h->launches;
-            }
-            --h->launches;
-        } else if (h->engine == 3) {
-            k_trimers<3><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat3b[h->device], nullptr, true, true);
-        } else if (h->engine == 1) {
-            k_trimers<1><<<gt, 256, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device], nullptr, true, true);
-        } else {
-            CUDA_TRY(h, load_coef_window(h->device, s));
-            k_trimers<0><<<gt, 256, 0, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, nullptr, nullptr, true, true);
-        }
+        if (h->engine == 4)
+            k_trimers<4><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_sym3b[h->device]);
+        else if (h->engine == 3)
+            k_trimers<3><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat3b[h->device]);
+        else
+            k_trimers<1><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
@@ -1334,17 +918,16 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
     auto ok = [&](cudaError_t e) { if (e != cudaSuccess) rc = MBPOL_B200_ECUDA; return e == cudaSuccess; };
     if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
-        const int eng = default_engine();
-        if (eng) { ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B)); }
-        else ok(load_coef_window(device, 0));
+        const int eng = default_engine(), eng2 = default_engine_2b();
+        ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B));
+        ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_trimers<4>, SMEM3B));
         if (nat3 == 18) {
-            if (eng == 3) k_eval_dimers<3><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
-            else if (eng) k_eval_dimers<1><<<(n + 255) / 256, 256, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);   // engine 2 -> 1 here
-            else k_eval_dimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
+            if (eng2 == 3) k_eval_dimers<3><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
+            else k_eval_dimers<1><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
         } else {
-            if (eng == 3) k_eval_trimers<3><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
-            else if (eng) k_eval_trimers<1><<<(n + 255) / 256, 256, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
-            else k_eval_trimers<0><<<(n + 255) / 256, 256>>>(n, dw, dE, dg, dfm, nullptr);
+            if (eng == 4) k_eval_trimers<4><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_sym3b[device]);
+            else if (eng == 3) k_eval_trimers<3><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
+            else k_eval_trimers<1><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
         }
         ok(cudaGetLastError());
         ok(cudaDeviceSynchronize());

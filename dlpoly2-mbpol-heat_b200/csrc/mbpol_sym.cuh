@@ -1,0 +1,71 @@
+// mbpol_sym.cuh -- engine 4 ("sym"): fat rows batched over a subgroup K of the molecule permutations of the 3B
+// polynomial (tools/gen_sym.py has the why and the format).
+//
+// A super row = the K-orbit of a fat row: |K| dynamic (w_j, v_j) pairs (row words, x reads and gradient read-modify-writes
+// in the per-thread shared-memory columns, exactly like engine 3) and ONE static body in which every coefficient of the
+// tape is loaded once and feeds 2|K| DFMAs on |K| independent chains -- image j works on the statically renamed registers
+// x[sigma_j(u)], x[sigma_j(c)], g[...].  Same staging as engines 1 and 3: cp.async double-buffered 16 KB chunks, broadcast
+// LDS.128, one loop over the super rows of a chunk with the shape dispatch inside.
+#pragma once
+#include "mbpol_tape.cuh"
+#ifndef MBPOL_SYM_HEADER
+#define MBPOL_SYM_HEADER "gen/sym_3b.h"
+#endif
+#include MBPOL_SYM_HEADER
+
+static_assert(SYM_CHUNK_DOUBLES == TAPE_CHUNK_DOUBLES, "engines 1, 3 and 4 share the staging buffers");
+extern __constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
+extern __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
+extern __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
+
+typedef TapeSmem<36> SymSmem;
+
+// x -> E = poly(x), g = dE/dx.  Must be called by ALL threads of a TAPE_BS-wide CTA (it contains barriers).
+__device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, double (&x)[36], double (&g)[36], double& E, SymSmem& sm)
+{
+    constexpr int NV = 36;
+    const unsigned* rowvars = c_sym_rowvars3b;
+    const unsigned tid = threadIdx.x;
+    const unsigned buf0 = (unsigned)__cvta_generic_to_shared(&sm.buf[0][0]);
+    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
+    const unsigned gs_delta = (unsigned)sizeof(sm.xs);
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        tape_sts(xs_t + c * TAPE_COL, x[c]);
+        tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
+        g[c] = 0.0;
+    }
+    tape_sts(xs_t + NV * TAPE_COL, 1.0);
+    tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
+    auto stage = [&](int k) {
+        const int t0 = c_sym_chunks3b[k][2], n = c_sym_chunks3b[k + 1][2] - t0;      // both even: 16-byte granules
+        const unsigned dst = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
+        for (int i = 2 * tid; i < n; i += 2 * TAPE_BS) tape_cp_async16(dst + 8 * i, tape + t0 + i);
+        tape_cp_commit();
+    };
+    stage(0);
+    double e = 0.0;
+    for (int k = 0; k < SYM3B_NCHUNKS; ++k) {
+        if (k + 1 < SYM3B_NCHUNKS) {
+            stage(k + 1);
+            tape_cp_wait<1>();
+        } else {
+            tape_cp_wait<0>();
+        }
+        __syncthreads();                                   // chunk k visible to every thread
+        unsigned cp = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
+        const unsigned row1 = c_sym_chunks3b[k + 1][1];
+        SYM_ROW_DECL
+        SYM_ROW_FETCH(c_sym_chunks3b[k][1])
+#pragma unroll 1
+        for (unsigned row = c_sym_chunks3b[k][1]; row < row1; ++row) {
+            SYM_ROW_PRE
+            SYM3B_ROW_SWITCH(shape)
+            SYM_ROW_POST
+        }
+        __syncthreads();                                   // everyone is done with this buffer before it is refilled
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);
+    E = e;
+}

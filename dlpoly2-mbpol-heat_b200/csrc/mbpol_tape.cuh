@@ -7,12 +7,15 @@
 // buffered 16 KB chunks) and read with broadcast LDS.128; one small counted loop per (chunk, type, u) segment with x_u and
 // the segment's g_u sum in registers, static register names for x[], g[]; the (w,v) word of a row comes from constant
 // memory; dynamic-index reads of x and updates of g go through per-thread columns in shared memory (32-bit shared
-// addresses).  Engine 2 (second half): the tape is read from the constant bank.  Engine 3 (mbpol_fat.cuh, default for the
-// 3B polynomial): the same machinery with all rows of one (w,v) prefix merged into a fat row.
+// addresses).  Engine 3 (mbpol_fat.cuh): the same machinery with all rows of one (w,v) prefix merged into a fat row.
+// (Two earlier engines -- straight-line PTX parts and a constant-bank tape -- were 1.6-2x slower and left the product
+// after round 1; experiments/README.md sections 1, 2 and 4 keep what was learnt from them.)
 #pragma once
 #include <cuda_runtime.h>
 
-#define TAPE_BS 256   /* threads per CTA: fixed (shared-memory column stride) */
+#ifndef TAPE_BS
+#define TAPE_BS 256   /* threads per CTA = shared-memory column stride; 256 / TAPE_BS CTAs per SM */
+#endif
 
 __device__ __forceinline__ double tape_lds(unsigned a)
 {
@@ -163,99 +166,6 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
             TAPE_SEG_END
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
-    }
-#pragma unroll
-    for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);
-    E = e;
-}
-
-
-// =========================================================================================================
-// Engine 2: the same rows, but the coefficient tape is read from the CONSTANT BANK (warp-uniform operands, no
-// 32-lane write-back through the LSU -- experiments/README.md section 2, last row).  The bank holds one window of
-// <= TAPE_CWINDOW_DOUBLES slots, so a polynomial takes NCPASS kernel launches; the host copies the next window into
-// mbpol_cwin between launches (stream ordered) and the partial (E, g) of every cluster travels through HBM.
-// No barriers: threads are independent here.
-// =========================================================================================================
-extern __constant__ double mbpol_cwin[TAPE_CWINDOW_DOUBLES];
-extern __constant__ unsigned c_tape_csegs2b[TAPE2B_NCSEGS];
-extern __constant__ unsigned c_tape_csegs3b[TAPE3B_NCSEGS];
-
-// Head of every constant window (16 bytes = two tape slots): the bounds of the pass.  Read from FIXED constant-bank
-// addresses so that ptxas can prove the loop trip counts warp-uniform (a function argument or a table lookup is not enough:
-// every tape load then falls from LDCU to the vector LDC path).
-struct TapeCPassHeader { int sg0, sg1; unsigned row0, row_last; };
-#define TAPE_CWINDOW_PAYLOAD (TAPE_CWINDOW_DOUBLES - 2)
-
-template <int NV>
-struct TapeCSmem {
-    double xs[NV + 1][TAPE_BS];
-    double gs[NV + 1][TAPE_BS];
-};
-
-#undef TAPE_LD2
-#undef TAPE_ROW_FETCH
-#undef TAPE_ROW_PRE
-#undef TAPE_ROW_POST
-#undef TAPE_ROWS_ADVANCE
-/* the tape pointer is a .const-space address kept opaque to the optimiser (inline PTX), so that ptxas sees a clean
-   warp-uniform chain  mov -> add imm -> ld.const [reg+imm]  and emits LDCU with a uniform-register base */
-/* not volatile: the window is read-only while a kernel runs, so the scheduler may hoist these loads across rows */
-#define TAPE_LD2(vx, vy, ca, imm) asm("ld.const.v2.f64 {%0, %1}, [%2+%3];" : "=d"(vx), "=d"(vy) : "l"(ca), "n"(imm))
-#define TAPE_ADVANCE(ca, bytes) asm("add.u64 %0, %0, %1;" : "+l"(ca) : "n"(bytes))
-#define TAPE_ROW_FETCH(ROWIDX)                                                                           \
-    {                                                                                                    \
-        TAPE_ROW_HEADER(ROWIDX)                                                                          \
-    }
-#define TAPE_ROW_PRE(ROWBYTES, S, K)                                                                     \
-    const unsigned aw_##S = nw_, av_##S = nv_;                                                           \
-    const double xw##S = nxw, xv##S = nxv;                                                               \
-    TAPE_PF_CLOADS(S, (K) * (ROWBYTES))                                                                  \
-    const double p2##S = xv##S * xw##S, P##S = p2##S * xu;                                               \
-    double S0##S = 0.0, S1##S = 0.0, S2##S = 0.0, S3##S = 0.0; /* a tape value must never be an FMA ADDEND: */ \
-    TAPE_ROW_FETCH(min(row + (K) + 1, row_last))   /* ptxas then drops the whole stream from LDCU to vector LDC */
-#define TAPE_ROW_POST(S)                                                                                 \
-    S0##S = (TAPE_SSUM(S)) + q0x##S;                                                                     \
-    TAPE_ROW_TAIL(S)
-#define TAPE_ROWS_ADVANCE(BYTES, N)                                                                      \
-    TAPE_ADVANCE(cp, BYTES);                                                                             \
-    row += (N);
-
-// One pass: adds the rows [row0, row_last] = segments [sg0, sg1) of one constant window to (E, g).  x must already be in
-// registers; g/E are accumulated into.  The bounds MUST arrive as kernel parameters: when they are looked up from a
-// table (even a constant-memory one indexed by a kernel parameter) ptxas no longer proves the loop trip counts
-// warp-uniform and moves every tape load from LDCU (uniform datapath) to the vector LDC path.
-template <int WHICH, int NV>
-__device__ __forceinline__ void tape_eval_const_pass(int sg0, int sg1, unsigned row0, unsigned row_last, double (&x)[NV], double (&g)[NV],
-                                                     double& E, TapeCSmem<NV>& sm)
-{
-    const unsigned* rowvars = (WHICH == 3) ? c_tape_rowvars3b : c_tape_rowvars2b;
-    const unsigned* segs = (WHICH == 3) ? c_tape_csegs3b : c_tape_csegs2b;
-    const unsigned tid = threadIdx.x;
-    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][tid]);
-    const unsigned gs_delta = (unsigned)sizeof(sm.xs);
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-        tape_sts(xs_t + c * TAPE_COL, x[c]);
-        tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
-    }
-    tape_sts(xs_t + NV * TAPE_COL, 1.0);
-    tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
-    double e = E;
-    // .const address of the current row; the first two slots of the window hold the pass bounds (see TapeCPassHeader)
-    unsigned long long cp = (unsigned long long)__cvta_generic_to_constant(mbpol_cwin) + 16;
-    unsigned row = row0;
-    unsigned nw_, nv_;
-    double nxw, nxv;
-    TAPE_ROW_FETCH(row)
-    for (int sg = sg0; sg < sg1; ++sg) {
-        TAPE_SEG_BEGIN(segs[sg])
-        if (WHICH == 3) {
-            TAPE3B_SEGMENT_SWITCH(type, nrows)
-        } else {
-            TAPE2B_SEGMENT_SWITCH(type, nrows)
-        }
-        TAPE_SEG_END
     }
 #pragma unroll
     for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -120,6 +121,52 @@ def test_fat_rows_reproduce_the_3b_polynomial(oracle):
         g[w] += Tw * xe[v]
         g[v] += Tw * xe[w]
     assert nmono == len(d["mono3b"])
+    Er, gr = oracle.poly("3b", a, x)
+    assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+    assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()
+
+
+@pytest.mark.parametrize("group", ["t", "z", "s3"])
+def test_symmetry_batched_rows_reproduce_the_3b_polynomial(oracle, group):
+    """tools/gen_sym.py: the super rows of engine 4 (fat rows batched over a subgroup K of the molecule permutations; one
+    coefficient a*|orbit|/|K| feeds |K| statically renamed images) are the same polynomial and gradient as the monomial
+    table -- checked in numpy from the generator's own structures, following the arithmetic of the generated code."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_poly
+    import gen_sym
+    d = np.load(gen_poly.DATA)
+    nv = 36
+    rows, shapes, vps = gen_sym.build(d["mono3b"], group)
+    K = len(vps)
+    assert K == {"t": 2, "z": 3, "s3": 6}[group] and len(shapes) <= 255
+    a = oracle.coef("3b")
+    rng = np.random.default_rng(13)
+    x = rng.uniform(0.1, 1.2, size=nv)
+    xe = np.concatenate([x, [1.0]])
+    E, g = 0.0, np.zeros(nv + 1)
+    nmono = 0
+    for (s, key, children) in rows:
+        assert tuple((us, tuple(cs for cs, _, _ in leaves)) for us, own, leaves in children) == shapes[s]
+        for j in range(K):
+            w, v = key[j]
+            p2 = xe[w] * xe[v]
+            Tw = 0.0
+            for (us, own, leaves) in children:
+                u = us[j]
+                P = p2 * xe[u]
+                S = a[own[0]] * own[1] / K if own else 0.0
+                for (cs, k, num) in leaves:
+                    c = cs[j]
+                    S += a[k] * num / K * xe[c]
+                    g[c] += a[k] * num / K * P
+                g[u] += S * p2
+                Tw += S * xe[u]
+            E += Tw * p2
+            g[w] += Tw * xe[v]
+            g[v] += Tw * xe[w]
+        for (us, own, leaves) in children:
+            nmono += sum(num for _, _, num in leaves) + (own[1] if own else 0)
+    assert nmono == len(d["mono3b"])          # every monomial exactly once (orbit sizes add up)
     Er, gr = oracle.poly("3b", a, x)
     assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
     assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()

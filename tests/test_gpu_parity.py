@@ -282,7 +282,7 @@ def test_bead_batched_matches_single_systems(mb, synth):
     assert c["trimers"] == ntri
 
 
-@pytest.mark.parametrize("engine", ["ptx", "tape", "ctape", "fat"])
+@pytest.mark.parametrize("engine", ["tape", "fat", "sym"])
 def test_every_polynomial_engine(engine):
     """The three selectable polynomial engines (MBPOL_B200_ENGINE) give the same physics: run the 64-water golden
     comparison in a fresh process per engine (the choice is read when a handle is created)."""

@@ -1,0 +1,255 @@
+#!/usr/bin/env python3
+"""Generate the SYMMETRY-BATCHED fat-row engine of the 3B polynomial (engine 4, csrc/mbpol_sym.cuh).
+
+Why.  ncu of the fat-row engine (tools/gen_fat.py): the FP64 pipe is 38 % busy and half of all DFMA stall samples are
+`short_scoreboard`, i.e. waiting for the broadcast LDS that delivers the next coefficient; one LDS.128 feeds only four
+DFMAs and ptxas keeps few of them in flight at 255 registers.  The polynomial is invariant under the permutations of the
+three water molecules (and of the two H of each water): a_{sigma(m)} = a_m.  So a subgroup K of that group is used to
+evaluate |K| monomials with ONE coefficient load:
+
+  * monomials are grouped into K-orbits; the trie roles (v, w = dynamic row pair, u = child, c = leaf) are chosen for ONE
+    representative per orbit and PROPAGATED to its images, so the fat rows come in K-orbits ("super rows") whose members
+    have identical coefficient tapes and differ only by a static renaming of x[] / g[] registers;
+  * a super row loads |K| dynamic (w,v) pairs and runs one body in which every coefficient feeds 2|K| DFMAs on |K|
+    independent chains:     for j < |K|:  S_kj += a x[sigma_j(c)];  g[sigma_j(c)] += a P_kj;
+  * a monomial fixed by an element of K is produced by several images: its tape value is a |orbit| / |K|.
+
+Only the molecule permutations are used (S3 or a subgroup): they cost 0.1-1.2 % extra monomial evaluations, an H swap 18 %.
+The variable order of the trie lists K-orbits of variables contiguously, which keeps the propagated trie as regular as
+the plain one (few distinct bodies, several super rows per body -- the bodies must be re-executed while they are still in
+the instruction cache, experiments/README.md section 2).
+
+Output: csrc/gen/sym_3b.h.  Same staging as engines 1 and 3 (cp.async double-buffered chunks, broadcast LDS.128).
+"""
+import argparse
+import collections
+import os
+
+import numpy as np
+
+import gen_poly as G
+
+CHUNK = 2048
+NV = 36
+UNIT = NV
+# atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
+V3A = [1, 4, 7, 0, 0, 3, 3, 6, 6, 1, 1, 1, 1, 2, 2, 2, 2, 4, 4, 5, 5, 0, 0, 0, 0, 3, 3, 3, 3, 6, 6, 6, 6, 0, 0, 3]
+V3B = [2, 5, 8, 1, 2, 4, 5, 7, 8, 4, 5, 7, 8, 4, 5, 7, 8, 7, 8, 7, 8, 4, 5, 7, 8, 1, 2, 7, 8, 1, 2, 4, 5, 3, 6, 6]
+
+
+def molperm(p):
+    """atom permutation that sends molecule m to molecule p[m]"""
+    return tuple(3 * p[a // 3] + a % 3 for a in range(9))
+
+
+def varperm(ap):
+    idx = {frozenset((a, b)): n for n, (a, b) in enumerate(zip(V3A, V3B))}
+    return tuple(idx[frozenset((ap[a], ap[b]))] for a, b in zip(V3A, V3B)) + (UNIT,)
+
+
+GROUPS = {   # static images sigma_j (as molecule permutations); image 0 is the identity
+    "1": [(0, 1, 2)],
+    "t": [(0, 1, 2), (1, 0, 2)],
+    "z": [(0, 1, 2), (1, 2, 0), (2, 0, 1)],
+    "s3": [(0, 1, 2), (1, 2, 0), (2, 0, 1), (1, 0, 2), (0, 2, 1), (2, 1, 0)],
+}
+
+
+def orbit_order(vps):
+    """variable order in which the K-orbits of variables are contiguous (orbits sorted by their smallest member)"""
+    seen, order = set(), []
+    for v in range(NV):
+        if v in seen:
+            continue
+        orb = []
+        for vp in vps:
+            if vp[v] not in orb:
+                orb.append(vp[v])
+        seen |= set(orb)
+        order.extend(orb)
+    return order
+
+
+def build(mono, group="t", reverse=True, repsel="max"):
+    """-> (super rows, shapes, vps).  super row = (shape id, [(w_j, v_j)], children); child = (us, own, leaves) with
+    us = (u_j), own = (coef index, num) or None, leaves = [((c_j), coef index, num)]; the tape value is a * num / |K|."""
+    vps = [varperm(molperm(p)) for p in GROUPS[group]]
+    K = len(vps)
+    order = orbit_order(vps)
+    if reverse:
+        order = order[::-1]
+    rank = {v: i for i, v in enumerate(order)}
+    monos = {}
+    for r in mono:
+        monos[tuple(sorted(int(v) for v in r[1:] if v >= 0))] = int(r[0])
+    pick = max if repsel == "max" else min
+    seen = set()
+    rows = collections.defaultdict(lambda: collections.defaultdict(lambda: [None, []]))
+    pend3 = []
+    for m, k in monos.items():
+        if m in seen:
+            continue
+        imgs = [tuple(sorted(vp[v] for v in m)) for vp in vps]
+        orbit = set(imgs)
+        assert all(monos[i] == k for i in orbit), "the monomial table is not invariant under the group"
+        seen |= orbit
+        rep = pick(orbit, key=lambda im: tuple(sorted((rank[v] for v in im), reverse=True)))
+        roles = sorted(rep, key=lambda v: rank[v], reverse=True)          # v, w, (u, (c))
+        num = len(orbit)
+        if len(roles) == 4:
+            v, w, u, c = roles
+            rows[tuple((vp[w], vp[v]) for vp in vps)][tuple(vp[u] for vp in vps)][1].append((tuple(vp[c] for vp in vps), k, num))
+        elif len(roles) == 3:
+            pend3.append((roles, k, num))
+        else:
+            v, w = roles
+            key = tuple((vp[w], vp[v]) for vp in vps)
+            assert rows[key][(UNIT,) * K][0] is None
+            rows[key][(UNIT,) * K][0] = (k, num)
+    for (v, w, u), k, num in pend3:     # degree 3: the own coefficient of child u if that child exists, else a leaf of the unit child
+        key = tuple((vp[w], vp[v]) for vp in vps)
+        us = tuple(vp[u] for vp in vps)
+        if us in rows[key]:
+            assert rows[key][us][0] is None
+            rows[key][us][0] = (k, num)
+        else:
+            rows[key][(UNIT,) * K][1].append((us, k, num))
+    shapes, out = {}, []
+    for key, ch in rows.items():
+        children = []
+        for us, (own, leaves) in sorted(ch.items()):
+            leaves.sort()
+            children.append((us, own, leaves))
+        shape = tuple((us, tuple(cs for cs, _, _ in leaves)) for us, own, leaves in children)
+        s = shapes.setdefault(shape, len(shapes))
+        out.append((s, list(key), children))
+    out.sort(key=lambda r: (r[0], r[1]))
+    return out, {s: sh for sh, s in shapes.items()}, vps
+
+
+def slots_of(shape):
+    n = sum(1 + len(ls) for us, ls in shape)
+    return n + (n % 2)
+
+
+def emit(rows, shapes, vps, ahead, nsum):
+    K = len(vps)
+    tape, rowvars = [], []
+    for (s, key, children) in rows:
+        start = len(tape)
+        for us, own, leaves in children:
+            tape.append(own if own else (-1, 0))
+            tape.extend((k, num) for cs, k, num in leaves)
+        if (len(tape) - start) % 2:
+            tape.append((-1, 0))
+        assert len(tape) - start == slots_of(shapes[s])
+        rowvars.extend(w | (v << 8) | (s << 16) for (w, v) in key)      # row words: dynamic variables of every image + shape
+    segs, chunks = [], []
+    used, pos, cur = CHUNK + 1, 0, None
+    for i, (s, key, children) in enumerate(rows):
+        n = slots_of(shapes[s])
+        assert n <= CHUNK
+        if used + n > CHUNK:
+            chunks.append((len(segs), i, pos))
+            used, cur = 0, None
+        if cur != s:
+            segs.append(s)
+            cur = s
+        segs[-1] += 1 << 8
+        used += n
+        pos += n
+    chunks.append((len(segs), len(rows), len(tape)))
+    nfp = 0
+    body_of = {}
+    for s, shape in shapes.items():
+        body, off = [], 0
+        npairs = slots_of(shape) // 2
+        loaded = [0]
+
+        def load_upto(n):
+            while loaded[0] < min(n, npairs):
+                k = loaded[0]
+                body.append("double q%dx, q%dy; TAPE_LDS_V2(q%dx, q%dy, cp, %d);" % (k, k, k, k, 16 * k))
+                loaded[0] += 1
+
+        def slot(i):
+            pair, lane = i // 2, i % 2
+            load_upto(pair + 1 + ahead)
+            return "q%d%s" % (pair, "xy"[lane])
+        load_upto(ahead)
+        for k, (us, ls) in enumerate(shape):
+            own = slot(off)
+            for j in range(K):
+                if us[j] != UNIT:
+                    body.append("const double P%d_%d = p2_%d * x[%d];" % (j, k, j, us[j]))
+            acc = [["S%d_%d_%d" % (j, k, n) for n in range(nsum)] for j in range(K)]
+            for j in range(K):
+                body.append("double %s = %s%s;" % (acc[j][0], own, "".join(", %s = 0.0" % a for a in acc[j][1:])))
+            for i, cs in enumerate(ls):
+                a = slot(off + 1 + i)
+                for j in range(K):
+                    pu = "p2_%d" % j if us[j] == UNIT else "P%d_%d" % (j, k)
+                    body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, %s, g[%d]);" % (acc[j][i % nsum], a, cs[j], acc[j][i % nsum], cs[j], a, pu, cs[j]))
+            nacc = max(1, min(nsum, len(ls)))
+            for j in range(K):
+                ssum = " + ".join(acc[j][:nacc])
+                if us[j] == UNIT:
+                    body.append("Tw_%d += %s;" % (j, ssum))
+                else:
+                    body.append("{ const double S_ = %s; g[%d] = fma(S_, p2_%d, g[%d]); Tw_%d = fma(S_, x[%d], Tw_%d); }" % (ssum, us[j], j, us[j], j, us[j], j))
+            off += 1 + len(ls)
+        body_of[s] = " ".join(body)
+    for (s, key, children) in rows:
+        nfp += K * (4 + sum(2 * len(ls) + (4 if us[0] != UNIT else 1) for us, own, ls in children))
+    Tg = "3B"
+    L = ["// generated by tools/gen_sym.py (|K| = %d static images) -- do not edit" % K, "#pragma once",
+         "#define SYM%s_NV %d" % (Tg, NV), "#define SYM%s_K %d" % (Tg, K), "#define SYM%s_NROWS %d" % (Tg, len(rows)),
+         "#define SYM%s_NTAPE %d" % (Tg, len(tape)), "#define SYM%s_NSEGS %d" % (Tg, len(segs)), "#define SYM%s_NCHUNKS %d" % (Tg, len(chunks) - 1),
+         "#define SYM%s_NSHAPES %d" % (Tg, len(shapes)), "#define SYM%s_FP64_INSTR %d" % (Tg, nfp), "#define SYM_CHUNK_DOUBLES %d" % CHUNK]
+    rv = rowvars + rowvars[-K:]       # one spare super row: the header of the next row is prefetched
+    L.append("static const unsigned SYM%s_ROWVARS_HOST[%d] = {%s};" % (Tg, len(rv), ",".join(str(w) for w in rv)))
+    L.append("static const unsigned SYM%s_SEGS_HOST[%d] = {%s};" % (Tg, len(segs), ",".join(str(w) for w in segs)))
+    L.append("// tape slot = coefficient index (< 0: zero) and numerator: value = a * num / |K|")
+    L.append("static const short SYM%s_COEFIDX_HOST[%d] = {%s};" % (Tg, len(tape), ",".join(str(c) for c, n in tape)))
+    L.append("static const unsigned char SYM%s_COEFNUM_HOST[%d] = {%s};" % (Tg, len(tape), ",".join(str(n) for c, n in tape)))
+    L.append("static const int SYM%s_CHUNKS_HOST[%d][3] = {%s};" % (Tg, len(chunks), ",".join("{%d,%d,%d}" % c for c in chunks)))
+    # row header macros for K images
+    L.append("#define SYM_ROW_DECL unsigned nshape, %s; double %s;" % (", ".join("nw_%d, nv_%d" % (j, j) for j in range(K)), ", ".join("nxw_%d, nxv_%d" % (j, j) for j in range(K))))
+    L.append("#define SYM_ROW_FETCH(ROWIDX) { %s }" % " ".join(
+        "{ const unsigned vw_ = rowvars[(ROWIDX) * %d + %d]; %snw_%d = xs_t + (vw_ & 255u) * TAPE_COL; nv_%d = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL; nxw_%d = tape_lds(nw_%d); nxv_%d = tape_lds(nv_%d); }"
+        % (K, j, "nshape = vw_ >> 16; " if j == 0 else "", j, j, j, j, j, j) for j in range(K)))
+    L.append("#define SYM_ROW_PRE const unsigned shape = nshape; %s SYM_ROW_FETCH(row + 1)" % " ".join(
+        "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
+        % (j, j, j, j, j, j, j, j, j, j, j, j) for j in range(K)))
+    L.append("#define SYM_ROW_POST %s" % " ".join(
+        "e = fma(Tw_%d, p2_%d, e); tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
+        % (j, j, j, j, j, j, j, j, j, j) for j in range(K)))
+    L.append("#define SYM%s_ROW_SWITCH(shape) { \\" % Tg)      # one loop over the super rows, dispatch inside (see tools/gen_fat.py)
+    for s in sorted(shapes):
+        nb = 8 * slots_of(shapes[s])
+        L.append("%sif ((shape) == %d) { %s cp += %d; } \\" % ("else " if s else "", s, body_of[s], nb))
+    L.append("}")
+    return "\n".join(L) + "\n", nfp, len(segs), len(chunks) - 1, len(tape)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--group", default=os.environ.get("SYM_GROUP", "t"), choices=sorted(GROUPS))
+    ap.add_argument("--forward", action="store_true", help="trie order = orbit order (default: reversed)")
+    ap.add_argument("--repsel", default=os.environ.get("SYM_REPSEL", "max"), choices=["max", "min"])
+    ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "6")))
+    ap.add_argument("--nsum", type=int, default=int(os.environ.get("SYM_NSUM", "1")))
+    ap.add_argument("--out", default=os.path.join(G.OUTD, "sym_3b.h"))
+    args = ap.parse_args()
+    d = np.load(G.DATA)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    rows, shapes, vps = build(d["mono3b"], args.group, not args.forward, args.repsel)
+    txt, nfp, nseg, nch, ntape = emit(rows, shapes, vps, args.ahead, args.nsum)
+    open(args.out, "w").write(txt)
+    code = sum(sum(len(ls) for us, ls in sh) for sh in shapes.values()) * len(vps)
+    print("3b: |K| = %d: %d super rows of %d shapes in %d segments / %d chunks, %d tape slots, %d FP64 instr per cluster, %d leaf pairs of code (largest body %d)" % (
+        len(vps), len(rows), len(shapes), nseg, nch, ntape, nfp, code, max(sum(len(ls) for us, ls in sh) for sh in shapes.values()) * len(vps)))
+
+
+if __name__ == "__main__":
+    main()
