@@ -7,6 +7,8 @@
 #include "mbpol_b200.h"
 #include "mbpol_device.cuh"
 
+extern __constant__ int c_gather_vp[3][36];  // slot s: variable n of the relabelled frame (molecules 0 <-> s swapped) -> original variable
+
 namespace mbpol_k {
 
 constexpr int NB2_CAP = 96;    // neighbours j>i within r2f (6.5 A): ~19 on average in liquid water
@@ -121,115 +123,220 @@ __device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict
     }
 }
 
-// accumulation of one evaluated trimer (mbpol.f90:896-1267): forces, per-atom energy, W, S; returns the block scalars
-__device__ __forceinline__ void trimer_scatter(const double (&r)[27], double E, const double (&cv)[36], const int (&o)[3],
-                                               const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr,
-                                               const OutPtrs& O, int flags, double (&sc)[8])
+// ---------------------------------------------------------------------------------------------------------
+// K3 phase 1: one thread per accepted trimer of this shard -- geometry, variables, switch, polynomial (the tape walk) and
+// a 40-double RECORD per trimer (trimer_record); nothing is scattered here.  The records of a CTA are staged through the
+// (now idle) column area of the shared memory and leave as coalesced 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------
+#define MBPOL_REC3_STRIDE 42      /* doubles between two staged records: 336 B, 16-byte aligned, spreads the banks */
+
+template <int ENGINE>
+__global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
+k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, CellInfo C,
+          const double* __restrict__ tape, double* __restrict__ rec)
 {
-    double g[27];
-    trimer_gradient(r, cv, g);
-    const double eu = MBPOL_ENGUNIT;
-    sc[0] = E * eu;
-#pragma unroll
-    for (int a = 0; a < 9; ++a) {
-        const int atom = o[a / 3] - 1 + (a % 3);
-        const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
-        atomicAdd(O.fx + atom, -gx);
-        atomicAdd(O.fy + atom, -gy);
-        atomicAdd(O.fz + atom, -gz);
-        sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
-        sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
-        sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const long long first = (long long)blockIdx.x * blockDim.x;
+    const long long t0_ = first + threadIdx.x;
+    const long long t = t0_ < ntri ? t0_ : ntri - 1;     // idle lanes shadow the last trimer: the tape walk has CTA barriers
+    const PolyCtx ctx{dyn_smem, tape};
+    double out[MBPOL_REC3];
+    {
+        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
+        double r[27], xv[36], gp[36], sw[4], Epoly;
+        trimer_geometry(nw, mono, C, mi, mj, mk, r);
+        trimer_x_switch(r, xv, sw);
+        poly3b_eval<ENGINE>(xv, gp, Epoly, ctx);
+        trimer_record(xv, gp, Epoly, sw, out);
     }
-    if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
-        const double e9 = (1.0 / 9.0) * E * eu;
+    __syncthreads();      // every thread has read its last gradient column: the column area is free
+    double* stage = reinterpret_cast<TapeSmem<36>*>(dyn_smem)->xs[0];
+    static_assert(sizeof(double) * MBPOL_REC3_STRIDE * TAPE_BS <= 2 * sizeof(double) * 37 * TAPE_BS, "staging area");
 #pragma unroll
-        for (int a = 0; a < 9; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e9);
-    }
-    if (flags & MBPOL_B200_WANT_FDECOMP) {
-        double xs[3] = {0, 0, 0}, xraw[27];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const int atom = o[a / 3] - 1 + (a % 3);
-            xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
-            xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
-        }
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            const double f[3] = {-(1.0 / 9.0) * g[3 * a] * eu, -(1.0 / 9.0) * g[3 * a + 1] * eu, -(1.0 / 9.0) * g[3 * a + 2] * eu};
-            scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 9, f);
-        }
-    }
-    if (flags & MBPOL_B200_WANT_ATOMIC_STRESS) {
-        // S_i(a,b) = 1/2*eu*sum_{j != i} (r_i-r_j)_a FM[i][j]_b with FM[i][j] = cv_n (r_i - r_j): a symmetric
-        // tensor cv_n d (x) d that goes to BOTH atoms of variable n (mbpol.f90:945-966)
-        double S[9][6];
-#pragma unroll
-        for (int a = 0; a < 9; ++a)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) S[a][q] = 0.0;
-#pragma unroll
-        for (int n = 0; n < 36; ++n) {
-            const int a = V3A[n], b = V3B[n];
-            const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
-            const double h = 0.5 * eu * cv[n];
-            const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { S[a][q] += T[q]; S[b][q] += T[q]; }
-        }
-        const size_t n = O.mxb;
-#pragma unroll
-        for (int a = 0; a < 9; ++a) {
-            double* p = O.astress + tensor_base(O, o[a / 3] - 1 + (a % 3));
-            atomicAdd(p + n * 0, S[a][0]); atomicAdd(p + n * 1, S[a][1]); atomicAdd(p + n * 2, S[a][2]);
-            atomicAdd(p + n * 3, S[a][1]); atomicAdd(p + n * 4, S[a][3]); atomicAdd(p + n * 5, S[a][4]);
-            atomicAdd(p + n * 6, S[a][2]); atomicAdd(p + n * 7, S[a][4]); atomicAdd(p + n * 8, S[a][5]);
-        }
+    for (int n = 0; n < MBPOL_REC3; ++n) stage[threadIdx.x * MBPOL_REC3_STRIDE + n] = out[n];
+    __syncthreads();
+    const long long left = ntri - first;
+    const int nvalid = left < (long long)blockDim.x ? (int)left : (int)blockDim.x;
+    double2* dst = reinterpret_cast<double2*>(rec + (size_t)first * MBPOL_REC3);
+    for (int i = threadIdx.x; i < nvalid * (MBPOL_REC3 / 2); i += blockDim.x) {
+        const int tr = i / (MBPOL_REC3 / 2), pr = i % (MBPOL_REC3 / 2);
+        dst[i] = *reinterpret_cast<const double2*>(stage + tr * MBPOL_REC3_STRIDE + 2 * pr);
     }
 }
 
-__device__ __forceinline__ void trimer_block_scalars(double (&sc)[8], const OutPtrs& O, int bead)
+#ifdef MBPOL_GATHER_KERNELS      /* non-template kernels: compiled in mbpol_kernels.cu only */
+// ---------------------------------------------------------------------------------------------------------
+// K3 phase 2: GATHER.  One warp per water w; the lanes walk the incidence list of w (every trimer of this shard that contains
+// w, with w's position in the sorted triple), rebuild the trimer's geometry exactly as phase 1 did, relabel the molecules
+// so that w comes first, turn the record into the force coefficients of the 21 variables that touch an atom of w and
+// accumulate w's share of everything do_trimer adds up (mbpol.f90:896-1267): forces, E/9 per atom, the force-decomposition
+// tensor W, the per-atom stress S, and the virial / stress / energy scalars.  One warp reduction per WATER, plain stores:
+// no FP64 atomics on per-atom data at all.
+// ---------------------------------------------------------------------------------------------------------
+__device__ constexpr int G3N = 21;          // variables with an atom of molecule 0: HH_a, OH_a (2), Ha-H (8), Oa-H (4), O-Ha (4), Oa-O (2)
+__device__ constexpr int G3VAR[G3N] = {0, 3, 4, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 29, 30, 33, 34};
+
+__device__ __forceinline__ double warp_sum(double v)
 {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restrict__ inc, const int* __restrict__ tri,
+                 const double* __restrict__ rec, const double* __restrict__ mono, const int* __restrict__ list,
+                 const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool active = w < nw;
+    const int beg = active ? inc_off[w] : 0, end = active ? inc_off[w + 1] : 0;
+    const bool want_e = flags & MBPOL_B200_WANT_ATOMIC_ENERGY, want_w = flags & MBPOL_B200_WANT_FDECOMP, want_s = flags & MBPOL_B200_WANT_ATOMIC_STRESS;
+    const double eu = MBPOL_ENGUNIT;
+    double G[9], A[27], S[18], sc[8], esum = 0.0;     // G = sum g (kcal/mol/A); A = sum X_c (x) g; S; scalars E, vir, stress(6)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) S[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = 0.0;
+    for (int i = beg + lane; i < end; i += 32) {
+        const unsigned code = inc[i];
+        const int t = (int)(code >> 2), s = (int)(code & 3u);
+        const int m3[3] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
+        double r0[27], r[27];
+        trimer_geometry(nw, mono, C, m3[0], m3[1], m3[2], r0);
+        // relabel: molecule 0 <-> molecule s
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const double v0 = r0[c], vm = r0[9 * m + c], vs = (s == 1) ? r0[9 + c] : ((s == 2) ? r0[18 + c] : r0[c]);
+                r[9 * m + c] = (m == 0) ? vs : ((m == s) ? v0 : vm);
+            }
+        const double* R = rec + (size_t)t * MBPOL_REC3;
+        const int* vp = c_gather_vp[s];
+        double g[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) g[q] = 0.0;
+#pragma unroll
+        for (int k = 0; k < G3N; ++k) {
+            const int n = G3VAR[k], a = V3A[n], b = V3B[n];
+            const double d0 = r[3 * a] - r[3 * b], d1 = r[3 * a + 1] - r[3 * b + 1], d2 = r[3 * a + 2] - r[3 * b + 2];
+            const double rinv = rsqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const int no = vp[n];
+            double cv = R[no];
+            if (n >= 33) cv += R[37 + no - 33];
+            cv *= rinv;
+            const double f0 = cv * d0, f1 = cv * d1, f2 = cv * d2;
+            if (a < 3) { g[3 * a] += f0; g[3 * a + 1] += f1; g[3 * a + 2] += f2; }
+            if (b < 3) { g[3 * b] -= f0; g[3 * b + 1] -= f1; g[3 * b + 2] -= f2; }
+            if (want_s) {   // S_i(a,b) += 1/2*eu*cv_n d (x) d for BOTH atoms of variable n (mbpol.f90:945-966)
+                const double h = 0.5 * eu * cv;
+                const double T[6] = {h * d0 * d0, h * d0 * d1, h * d0 * d2, h * d1 * d1, h * d1 * d2, h * d2 * d2};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    if (a < 3) S[6 * a + q] += T[q];
+                    if (b < 3) S[6 * b + q] += T[q];
+                }
+            }
+        }
+        const double E = R[36];
+        if (s == 0) sc[0] += E * eu;                   // every trimer has exactly one slot-0 incidence
+        esum += E;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
+            G[3 * a] += g[3 * a]; G[3 * a + 1] += g[3 * a + 1]; G[3 * a + 2] += g[3 * a + 2];
+            sc[1] += r[3 * a] * gx + r[3 * a + 1] * gy + r[3 * a + 2] * gz;
+            sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
+            sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
+        }
+        if (want_w) {   // X_c = sum of the RAW coordinates of the 9 atoms of the cluster
+            double X[3] = {0, 0, 0};
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int o = list[3 * m3[m]] - 1;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { X[0] += xr[o + k]; X[1] += yr[o + k]; X[2] += zr[o + k]; }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) A[9 * a + i + 3 * j] += X[i] * g[3 * a + j];
+        }
+    }
+    // one reduction per water
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = warp_sum(G[i]);
+    esum = warp_sum(esum);
+    if (want_w) {
+#pragma unroll
+        for (int i = 0; i < 27; ++i) A[i] = warp_sum(A[i]);
+    }
+    if (want_s) {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) S[i] = warp_sum(S[i]);
+    }
+    if (active && lane == 0 && end > beg) {
+        const int o = list[3 * w] - 1;                  // 0-based O index; H at o+1, o+2 (mbpol.f90:592-594)
+        const size_t n = O.mxb;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int atom = o + a;
+            O.fx[atom] -= G[3 * a] * eu; O.fy[atom] -= G[3 * a + 1] * eu; O.fz[atom] -= G[3 * a + 2] * eu;
+            if (want_e) O.aeng[atom] += (1.0 / 9.0) * esum * eu;
+            if (want_w) {   // W_i = sum_c (9 x_i - X_c) (x) (-g_i eu / 9) = -x_i (x) G_i eu + A_i eu / 9
+                const double x3[3] = {xr[atom], yr[atom], zr[atom]};
+                double* p = O.afd + tensor_base(O, atom);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) p[n * (i + 3 * j)] += (1.0 / 9.0) * eu * A[9 * a + i + 3 * j] - x3[i] * G[3 * a + j] * eu;
+            }
+            if (want_s) {
+                double* p = O.astress + tensor_base(O, atom);
+                const double* q = S + 6 * a;
+                p[n * 0] += q[0]; p[n * 1] += q[1]; p[n * 2] += q[2];
+                p[n * 3] += q[1]; p[n * 4] += q[3]; p[n * 5] += q[4];
+                p[n * 6] += q[2]; p[n * 7] += q[4]; p[n * 8] += q[5];
+            }
+        }
+    }
+    // scalars: E, virial, stress of this shard (per bead)
+    const int bead = active ? w / O.nwb : -1;          // (thread 0 of every launched block owns a water)
     double v2[2] = {sc[0], sc[1]};
     block_reduce_add_bead<2>(v2, O.scal, S_ENG3, bead);
     double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
     block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
 }
 
-template <int ENGINE>
-__global__ void __launch_bounds__(TAPE_BS, 256 / TAPE_BS)
-k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-          const double* __restrict__ tape)
+// incidence lists: water -> (trimer << 2 | slot) for the trimers [0, ntri) of this shard
+__global__ void k_inc_count(long long ntri, const int* __restrict__ tri, int* __restrict__ cnt)
 {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t0_ < ntri;
-    const long long t = valid ? t0_ : ntri - 1;     // idle lanes shadow the last trimer: the tape walk has CTA barriers
-    const PolyCtx ctx{dyn_smem, tape};
-    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // E, virial, stress xx xy xz yy yz zz
-    int bead = -1;
-    {
-        const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
-        if (valid) bead = mi / O.nwb;
-        double r[27];
-        double E, cv[36];
-        auto geom = [&](double (&rr)[27], bool again) {
-            if (again) trimer_geometry<true>(nw, mono, C, mi, mj, mk, rr);
-            else trimer_geometry<false>(nw, mono, C, mi, mj, mk, rr);
-        };
-        trimer_eval_regeom<ENGINE>(geom, r, E, cv, ctx);
-        const int o[3] = {list[3 * mi], list[3 * mj], list[3 * mk]};   // 1-based O indices; H at o+1, o+2 (mbpol.f90:592-594)
-        if (valid) trimer_scatter(r, E, cv, o, xr, yr, zr, O, flags, sc);
-    }
-    trimer_block_scalars(sc, O, bead);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * ntri) atomicAdd(&cnt[tri[i]], 1);
 }
+__global__ void k_inc_fill(long long ntri, const int* __restrict__ tri, const int* __restrict__ off, int* __restrict__ cur, unsigned* __restrict__ inc)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * ntri) return;
+    const int w = tri[i];
+    inc[off[w] + atomicAdd(&cur[w], 1)] = (unsigned)((i / 3) << 2) | (unsigned)(i % 3);
+}
+
+#endif   // MBPOL_GATHER_KERNELS
 
 // ---------------------------------------------------------------------------------------------------------
 // K2: dimers
 // ---------------------------------------------------------------------------------------------------------
 template <int ENGINE>
-__global__ void __launch_bounds__(TAPE_BS, 256 / TAPE_BS)
+__global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
 k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
          const double* __restrict__ tape)
@@ -327,7 +434,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
 // batched per-cluster kernels (legacy ABI / KAT tests)
 // ---------------------------------------------------------------------------------------------------------
 template <int ENGINE>
-__global__ void __launch_bounds__(TAPE_BS, 256 / TAPE_BS) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
+__global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1) k_eval_dimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const PolyCtx ctx{dyn_smem, tape};
@@ -344,7 +451,7 @@ __global__ void __launch_bounds__(TAPE_BS, 256 / TAPE_BS) k_eval_dimers(int n, c
 }
 
 template <int ENGINE>
-__global__ void __launch_bounds__(TAPE_BS, 256 / TAPE_BS) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
+__global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1) k_eval_trimers(int n, const double* __restrict__ w, double* E, double* g, double* fm, const double* __restrict__ tape)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const PolyCtx ctx{dyn_smem, tape};

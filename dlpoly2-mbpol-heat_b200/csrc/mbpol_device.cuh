@@ -128,6 +128,43 @@ __device__ __forceinline__ void trimer_rinv(const double (&r)[27], double (&rinv
     }
 }
 
+// Phase 1 of the box path (k_trimers): variables and the switch, everything the record of a trimer needs besides the
+// polynomial.  sw[0] = s = sab sac + sab sbc + sac sbc, sw[1..3] = ds/dr_ab, ds/dr_ac, ds/dr_bc (mbpol-3b-poly.cpp:231-235, 292-301)
+__device__ __forceinline__ void trimer_x_switch(const double (&r)[27], double* xv, double (&sw)[4])
+{
+    double doo[3];
+#pragma unroll
+    for (int n = 0; n < 36; ++n) {
+        const int a = 3 * V3A[n], b = 3 * V3B[n];
+        const double dx = r[a] - r[b], dy = r[a + 1] - r[b + 1], dz = r[a + 2] - r[b + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        if (n >= 33) doo[n - 33] = d;
+        xv[n] = exp(-mbpol_par.k3[V3K[n]] * (d - mbpol_par.d3[V3K[n]]));
+    }
+    double gab, gac, gbc;
+    const double sab = switch_fn(doo[0], mbpol_par.r3i, mbpol_par.r3f, gab);
+    const double sac = switch_fn(doo[1], mbpol_par.r3i, mbpol_par.r3f, gac);
+    const double sbc = switch_fn(doo[2], mbpol_par.r3i, mbpol_par.r3f, gbc);
+    sw[0] = sab * sac + sab * sbc + sac * sbc;
+    sw[1] = gab * (sac + sbc);
+    sw[2] = gac * (sab + sbc);
+    sw[3] = gbc * (sab + sac);
+}
+
+// The record phase 1 leaves per trimer (MBPOL_REC3 doubles): rec[n] = -k_n (dEpoly/dx_n s) x_n for the 36 variables,
+// rec[36] = s Epoly (the 3B energy, kcal/mol), rec[37..39] = Epoly ds/dr_OO.  Phase 2 (k_trimers_gather) only multiplies by
+// 1/d_n:  cv[n] = rec[n] / d_n (+ rec[37 + n - 33] / d_n for the three O-O variables) -- trimer_finish split in two.
+#define MBPOL_REC3 40
+__device__ __forceinline__ void trimer_record(const double* xv, const double* gp, double Epoly, const double (&sw)[4], double (&rec)[MBPOL_REC3])
+{
+#pragma unroll
+    for (int n = 0; n < 36; ++n) rec[n] = -mbpol_par.k3[V3K[n]] * (gp[n] * sw[0]) * xv[n];
+    rec[36] = sw[0] * Epoly;
+    rec[37] = sw[1] * Epoly;
+    rec[38] = sw[2] * Epoly;
+    rec[39] = sw[3] * Epoly;
+}
+
 // switch + chain rule: (x, dEpoly/dx, Epoly) -> E and the per-variable force coefficients cv
 __device__ __forceinline__ void trimer_finish(const double* xv, const double* gp, double Epoly, const double (&rinv)[36], double& E,
                                               double (&cv)[36])

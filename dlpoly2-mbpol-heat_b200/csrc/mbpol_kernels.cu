@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "mbpol_b200.h"
+#define MBPOL_GATHER_KERNELS
 #include "mbpol_cluster.cuh"
 #include "gen/mbpol_model_data.h"
 #include <cstdlib>
@@ -42,6 +43,7 @@ __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
 __constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
 __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
+__constant__ int c_gather_vp[3][36];
 
 using namespace mbpol_k;
 
@@ -49,9 +51,9 @@ using namespace mbpol_k;
 namespace mbpol_k {
 extern template __global__ void k_dimers<1>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
 extern template __global__ void k_dimers<3>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_trimers<1>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_trimers<3>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_trimers<4>(long long, const int*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_trimers<1>(long long, const int*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_trimers<3>(long long, const int*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_trimers<4>(long long, const int*, int, const double*, CellInfo, const double*, double*);
 extern template __global__ void k_eval_dimers<1>(int, const double*, double*, double*, double*, const double*);
 extern template __global__ void k_eval_dimers<3>(int, const double*, double*, double*, double*, const double*);
 extern template __global__ void k_eval_trimers<1>(int, const double*, double*, double*, double*, const double*);
@@ -352,7 +354,7 @@ int default_engine_2b()
     if (e && std::string(e) == "fat") return 3;
     return MBPOL_DEFAULT_ENGINE_2B;
 }
-constexpr size_t SMEM2B = sizeof(TapeSmem<31>), SMEM3B = sizeof(TapeSmem<36>);
+constexpr size_t SMEM2B = tape_smem_bytes(31, MBPOL_BS2, TAPE_CHUNK_DOUBLES), SMEM3B = tape_smem_bytes(36, MBPOL_BS3, TAPE_CHUNK_DOUBLES);
 
 template <class K>
 cudaError_t allow_smem(K kernel, size_t bytes)
@@ -434,6 +436,21 @@ int upload_constants(int device)
         if (cudaMemcpyToSymbol(c_sym_chunks3b, SYM3B_CHUNKS_HOST, sizeof(SYM3B_CHUNKS_HOST)) != cudaSuccess) return 1;
     }
     if (cudaMemcpyToSymbol(mbpol_par, &P, sizeof(P)) != cudaSuccess) return 1;
+    {   // gather kernel: variable relabelling when molecules 0 and s of a trimer are swapped
+        static const int va[36] = {1, 4, 7, 0, 0, 3, 3, 6, 6, 1, 1, 1, 1, 2, 2, 2, 2, 4, 4, 5, 5, 0, 0, 0, 0, 3, 3, 3, 3, 6, 6, 6, 6, 0, 0, 3};
+        static const int vb[36] = {2, 5, 8, 1, 2, 4, 5, 7, 8, 4, 5, 7, 8, 4, 5, 7, 8, 7, 8, 7, 8, 4, 5, 7, 8, 1, 2, 7, 8, 1, 2, 4, 5, 3, 6, 6};
+        int vp[3][36];
+        for (int s = 0; s < 3; ++s)
+            for (int n = 0; n < 36; ++n) {
+                auto q = [&](int a) { const int m = a / 3, mm = (m == 0) ? s : ((m == s) ? 0 : m); return 3 * mm + a % 3; };
+                const int a = q(va[n]), b = q(vb[n]);
+                vp[s][n] = -1;
+                for (int k = 0; k < 36; ++k)
+                    if ((va[k] == a && vb[k] == b) || (va[k] == b && vb[k] == a)) vp[s][n] = k;
+                if (vp[s][n] < 0) return 1;
+            }
+        if (cudaMemcpyToSymbol(c_gather_vp, vp, sizeof(vp)) != cudaSuccess) return 1;
+    }
     return 0;
 }
 
@@ -475,8 +492,9 @@ struct mbpol_b200_handle {
     CellInfo C;
     Grid G;
     int ncells = 0;
-    DevBuf<double> xyz, vel, mono, out;
-    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag;
+    DevBuf<double> xyz, vel, mono, out, rec;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
+    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur;
+    DevBuf<unsigned> inc;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll;
     DevBuf<char> scan_tmp;
@@ -713,24 +731,36 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     OutPtrs O = h->views();
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     if (h->nd_shard > 0) {
-        const unsigned gd = (unsigned)((h->nd_shard + TAPE_BS - 1) / TAPE_BS);
+        const unsigned gd = (unsigned)((h->nd_shard + MBPOL_BS2 - 1) / MBPOL_BS2);
         const int2* dl = h->dimers.p + d0;
         if (h->engine2b == 3)
-            k_dimers<3><<<gd, TAPE_BS, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
+            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
         else
-            k_dimers<1><<<gd, TAPE_BS, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
+            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     if (h->nt_shard > 0) {
-        const unsigned gt = (unsigned)((h->nt_shard + TAPE_BS - 1) / TAPE_BS);
+        const unsigned gt = (unsigned)((h->nt_shard + MBPOL_BS3 - 1) / MBPOL_BS3);
         const int* tl = h->trimers.p + 3 * t0;
+        // incidence lists of the shard: count -> exclusive scan -> fill
+        CUDA_TRY(h, h->rec.reserve((size_t)h->nt_shard * MBPOL_REC3));
+        CUDA_TRY(h, h->inc.reserve((size_t)3 * h->nt_shard));
+        CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
+        const unsigned gi = (unsigned)((3 * h->nt_shard + 255) / 256);
+        k_inc_count<<<gi, 256, 0, s>>>(h->nt_shard, tl, h->inc_off.p);
+        if (int rc = scan_int(h, h->inc_off.p, h->inc_off.p, nw + 1)) return rc;
+        k_inc_fill<<<gi, 256, 0, s>>>(h->nt_shard, tl, h->inc_off.p, h->inc_cur.p, h->inc.p);
         if (h->engine == 4)
-            k_trimers<4><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_sym3b[h->device]);
+            k_trimers<4><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_sym3b[h->device], h->rec.p);
         else if (h->engine == 3)
-            k_trimers<3><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat3b[h->device]);
+            k_trimers<3><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_fat3b[h->device], h->rec.p);
         else
-            k_trimers<1><<<gt, TAPE_BS, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape3b[h->device]);
+            k_trimers<1><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_tape3b[h->device], h->rec.p);
+        k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, tl, h->rec.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        h->launches += 4;
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
@@ -922,12 +952,12 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
         ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B));
         ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_trimers<4>, SMEM3B));
         if (nat3 == 18) {
-            if (eng2 == 3) k_eval_dimers<3><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
-            else k_eval_dimers<1><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
+            if (eng2 == 3) k_eval_dimers<3><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
+            else k_eval_dimers<1><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
         } else {
-            if (eng == 4) k_eval_trimers<4><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_sym3b[device]);
-            else if (eng == 3) k_eval_trimers<3><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
-            else k_eval_trimers<1><<<(n + TAPE_BS - 1) / TAPE_BS, TAPE_BS, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
+            if (eng == 4) k_eval_trimers<4><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_sym3b[device]);
+            else if (eng == 3) k_eval_trimers<3><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
+            else k_eval_trimers<1><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
         }
         ok(cudaGetLastError());
         ok(cudaDeviceSynchronize());

@@ -13,8 +13,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// threads per CTA = stride of the per-thread shared-memory columns.  The 2B and the 3B kernels may use different sizes
+// (MBPOL_BS2 / MBPOL_BS3, csrc/Makefile): every translation unit instantiates kernels of ONE family and defines TAPE_BS
+// accordingly before including this file (mbpol_inst.cu); the host code launches with MBPOL_BS2 / MBPOL_BS3.
+#ifndef MBPOL_BS2
+#define MBPOL_BS2 256
+#endif
+#ifndef MBPOL_BS3
+#define MBPOL_BS3 256
+#endif
 #ifndef TAPE_BS
-#define TAPE_BS 256   /* threads per CTA = shared-memory column stride; 256 / TAPE_BS CTAs per SM */
+#define TAPE_BS MBPOL_BS3
 #endif
 
 __device__ __forceinline__ double tape_lds(unsigned a)
@@ -96,6 +105,8 @@ extern __constant__ unsigned c_tape_segs2b[TAPE2B_NSEGS];
 extern __constant__ unsigned c_tape_segs3b[TAPE3B_NSEGS];
 extern __constant__ int c_tape_chunks2b[TAPE2B_NCHUNKS + 1][3];
 extern __constant__ int c_tape_chunks3b[TAPE3B_NCHUNKS + 1][3];
+
+constexpr size_t tape_smem_bytes(int nv, int bs, int chunk_doubles) { return (size_t)16 * chunk_doubles + (size_t)16 * (nv + 1) * bs; }
 
 template <int NV>
 struct TapeSmem {   // dynamic shared memory layout

@@ -70,7 +70,7 @@ def orbit_order(vps):
     return order
 
 
-def build(mono, group="t", reverse=True, repsel="max"):
+def build(mono, group="z", reverse=True, repsel="max"):
     """-> (super rows, shapes, vps).  super row = (shape id, [(w_j, v_j)], children); child = (us, own, leaves) with
     us = (u_j), own = (coef index, num) or None, leaves = [((c_j), coef index, num)]; the tape value is a * num / |K|."""
     vps = [varperm(molperm(p)) for p in GROUPS[group]]
@@ -234,7 +234,7 @@ def emit(rows, shapes, vps, ahead, nsum):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--group", default=os.environ.get("SYM_GROUP", "t"), choices=sorted(GROUPS))
+    ap.add_argument("--group", default=os.environ.get("SYM_GROUP", "z"), choices=sorted(GROUPS))
     ap.add_argument("--forward", action="store_true", help="trie order = orbit order (default: reversed)")
     ap.add_argument("--repsel", default=os.environ.get("SYM_REPSEL", "max"), choices=["max", "min"])
     ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "6")))
