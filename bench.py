@@ -36,17 +36,19 @@ def shard_range(total, rank, nranks):
     return total * rank // nranks, total * (rank + 1) // nranks
 
 
-def pack_outputs(out, mxatms):
-    """Host mirror of the packed device buffer layout (include/mbpol_b200.h): per-atom arrays then 32 scalars."""
+def pack_outputs(out, mxatms, nranks=1):
+    """Host mirror of the packed device buffer layout (include/mbpol_b200.h): per-atom arrays, padding to nranks chunks, 32 scalars."""
     n = mxatms
-    buf = np.zeros(22 * n + 32)
+    chunk = (22 * n + nranks - 1) // nranks
+    chunk += chunk & 1
+    buf = np.zeros(chunk * nranks + 32)
     buf[0:n], buf[n:2 * n], buf[2 * n:3 * n] = out["fxx"], out["fyy"], out["fzz"]
     buf[3 * n:4 * n] = out["atomic_energy"]
     if out.get("atomic_stress") is not None:
         buf[4 * n:13 * n] = out["atomic_stress"]
     if out.get("atomic_fdecomp") is not None:
         buf[13 * n:22 * n] = out["atomic_fdecomp"]
-    s = buf[22 * n:]
+    s = buf[chunk * nranks:]
     s[0], s[1], s[2], s[3] = out["eng2"], out["vir2"], out["eng3"], out["vir3"]
     s[4:13] = out["stress"]
     return buf
@@ -104,12 +106,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU evaluators (oracle/_ref) under the restated list-driven driver
 # ------------------------------------------------------------------------------------------------------------
-def reference_sample(box, threads, n_trimers_sample):
+def reference_sample(box, threads, n_trimers_sample, flags=7):
     """One bounded CPU step: S trimers plus the proportional number of dimers.  Returns (seconds, trimers, info)."""
     from oracle.oracle import Oracle
     o = Oracle()
     kind = "reference" if o.have_reference else "port"
-    out = o.forces(box, mode="listed", use_ref=o.have_reference, nthreads=threads, want_stress=False, want_fdecomp=True,
+    out = o.forces(box, mode="listed", use_ref=o.have_reference, nthreads=threads, want_stress=bool(flags & 4), want_fdecomp=bool(flags & 2),
                    want_lists=False, max_clusters=n_trimers_sample)
     nt, nd = out["ntrimer"], out["ndimer"]
     st, sd = min(nt, n_trimers_sample), min(nd, n_trimers_sample)
@@ -126,11 +128,11 @@ def run_reference(args, box, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample or 4000 * threads
+    sample = args.cpu_sample or max(4000 * threads, 20000)       # >= 20 k clusters per step: the per-dimer figure is stable
     vals = []
     info = {}
     for it in range(args.warmup + args.steps):
-        t, st, info = reference_sample(box, threads, sample)
+        t, st, info = reference_sample(box, threads, sample, args.flags)
         if it >= args.warmup:
             vals.append((t, st))
     tsum = sum(v[0] for v in vals)
@@ -154,7 +156,8 @@ def workload_config(box, args, nd, nt):
     return {"workload": "%d H2O MB-pol box (cubic, L=%.2f A, seed %d): 2B+3B energies, forces, per-atom energy and "
                         "force-decomposition tensor%s, heat-flux contractions" % (box["nw"], box["L"], box["seed"], " and per-atom stress" if args.flags & 4 else ""),
             "n_waters": box["nw"], "n_dimers": int(nd), "n_trimers": int(nt), "flags": args.flags,
-            "parallelism": "work-list shards x%d, replicated coordinates, one all-reduce" % args.gpus,
+            "parallelism": "water-range shards x%d (each rank builds and evaluates its own lists), replicated coordinates, in-library NCCL reduce-scatter" % args.gpus,
+            "host_threads": os.cpu_count(),
             "l2": "flushed between timed steps (256 MiB memset)"}
 
 
@@ -318,23 +321,34 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = box["mxatms"]
     h = mb.mbpol_init(box["nttm2"], flags=args.flags, device=local)
-    mb.mbpol_set_shard(h, rank, world)
+    if world > 1:      # the library owns the communicator of the data path: unique id from rank 0, shipped with torch.distributed
+        uid = torch.zeros(mb.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(mb.mbpol_comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        mb.mbpol_comm_init(h, rank, world, bytes(uid.cpu().numpy().tobytes()))
     stream = torch.cuda.ExternalStream(mb.mbpol_stream(h), device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    vel = (box["vxx"], box["vyy"], box["vzz"])
-    want_s = bool(args.flags & 4)
+    want_e, want_w, want_s = bool(args.flags & 1), bool(args.flags & 2), bool(args.flags & 4)
+
+    def pinned(a):      # the caller's arrays live in pinned host memory (registered once, as a host code would do at start-up)
+        t = torch.empty(a.shape, dtype=torch.float64).pin_memory()
+        v = t.numpy()
+        v[...] = a
+        keep.append(t)
+        return v
+    keep = []
+    X, Y, Z, VX, VY, VZ = (pinned(box[k]) for k in ("xxx", "yyy", "zzz", "vxx", "vyy", "vzz"))
+    vel = (VX, VY, VZ)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -------------------------------------------------------------------------
-    mb.mbpol_upload(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"], *vel)
+    # ---- device-resident timing: list build + 2B + 3B + flux + (N > 1) the in-library NCCL reduction ---------------------------
+    mb.mbpol_upload(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], X, Y, Z, *vel)
     mb.mbpol_compute(h)
-    ptr, cnt = mb.mbpol_device_outputs(h)
-    packed = torch.as_tensor(DeviceArray(ptr, cnt), device="cuda")
-    counts = mb.mbpol_counts(h)
     k3 = []
 
     def step():
@@ -343,11 +357,9 @@ def main():
             flush.zero_()
             e0.record(stream)
             mb.mbpol_compute(h)
-            if world > 1:
-                allreduce_packed(packed)
             e1.record(stream)
         e1.synchronize()
-        k3.append(mb.mbpol_kernel_times(h))
+        k3.append(mb.mbpol_phase_times(h))
         return e0.elapsed_time(e1)
 
     for _ in range(args.warmup):
@@ -359,38 +371,39 @@ def main():
     k3.clear()
     ms = [step() for _ in range(args.steps)]
     barrier()
+    counts = mb.mbpol_counts(h)
     t_dev = torch.tensor([sum(ms) / len(ms)], dtype=torch.float64, device="cuda")
-    t3 = torch.tensor([np.mean([k["k3b_ms"] for k in k3])], dtype=torch.float64, device="cuda")
+    t3 = torch.tensor([np.mean([k["k_trimers_ms"] for k in k3])], dtype=torch.float64, device="cuda")
+    nts = torch.tensor([counts["trimers_shard"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        both = torch.cat([t3, nts])
+        gathered = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(gathered, both)
+        slow = max(gathered, key=lambda g: float(g[0]))      # the roofline kernel of the slowest rank
+        t3, nts = slow[0:1], slow[1:2]
     ms_step = float(t_dev.item())
-    launches = int(k3[-1]["launches"]) * args.steps
+    launches = int(mb.mbpol_kernel_times(h)["launches"]) * args.steps
 
     # ---- end-to-end through the public call (host buffers, copies inside the timed region) ------------------
-    outs = {k: np.zeros(n) for k in ("fxx", "fyy", "fzz", "ae")}
-    afd = np.zeros(9 * n) if args.flags & 2 else None
-    ast = np.zeros(9 * n) if want_s else None
+    outs = {k: pinned(np.zeros(n)) for k in ("fxx", "fyy", "fzz")}
+    ae = pinned(np.zeros(n)) if want_e else None
+    afd = pinned(np.zeros(9 * n)) if want_w else None
+    ast = pinned(np.zeros(9 * n)) if want_s else None
     stress = np.zeros(9)
 
     def e2e_step():
         t0 = time.perf_counter()
-        if world > 1:
-            mb.mbpol_upload(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"], *vel)
-            mb.mbpol_compute(h)
-            with torch.cuda.stream(stream):
-                allreduce_packed(packed)
-            stream.synchronize()
-            r = mb.mbpol_download(h, outs["fxx"], outs["fyy"], outs["fzz"], stress=stress, atomic_energy=outs["ae"],
-                                  atomic_stress=ast, atomic_fdecomp=afd)
-        else:
-            r = mb.mbpol_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["xxx"], box["yyy"], box["zzz"],
-                                outs["fxx"], outs["fyy"], outs["fzz"], stress=stress, atomic_energy=outs["ae"], atomic_stress=ast,
-                                atomic_fdecomp=afd, vxx=vel[0], vyy=vel[1], vzz=vel[2])
+        r = mb.mbpol_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], X, Y, Z,
+                            outs["fxx"], outs["fyy"], outs["fzz"], stress=stress, atomic_energy=ae, atomic_stress=ast,
+                            atomic_fdecomp=afd, vxx=vel[0], vyy=vel[1], vzz=vel[2])
         return time.perf_counter() - t0, r
 
     for _ in range(2):
         e2e_step()
+    for v in list(outs.values()) + [a for a in (ae, afd, ast) if a is not None]:
+        v[...] = 0.0
+    stress[...] = 0.0
     barrier()
     te = []
     for _ in range(args.steps):
@@ -401,43 +414,90 @@ def main():
     t_e2e = torch.tensor([float(np.mean(te))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    narr = 3 + (1 if want_e else 0) + (9 if want_w else 0) + (9 if want_s else 0)
     h2d = 8 * n * 6 + 4 * box["nttm2"]
-    d2h = 8 * (n * (4 + (9 if afd is not None else 0) + (9 if ast is not None else 0)) + 32)
+    d2h = 8 * (n * narr // world + 32)       # reduce-scatter: every rank returns its 1/N slice of the requested arrays
+
+    # the e2e accumulators of all ranks, summed like the host's gdsum would: `steps` times the result of one step
+    acc = np.concatenate([outs["fxx"], outs["fyy"], outs["fzz"]] + [a for a in (ae, afd, ast) if a is not None] +
+                         [stress, [res["eng2"], res["eng3"], res["vir2"], res["vir3"]]])
+    if world > 1:
+        tacc = torch.from_numpy(acc).cuda()
+        dist.all_reduce(tacc)
+        acc = tacc.cpu().numpy()
 
     if rank == 0:
         nt, nd = counts["trimers"], counts["dimers"]
         peak = mb.measure_fp64_peak()
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_k_trimers_traffic.json")
-        if world == 1 and args.nw == 32768 and os.path.exists(tpath):      # ncu --set full capture of the same launch
+        tpath = os.path.join(ROOT, "profiles", "r2_k_trimers_traffic.json")
+        if args.nw == 32768 and os.path.exists(tpath):      # ncu --set full capture of this build's k_trimers launch (profiles/)
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            if traffic is not None and world > 1:
+                traffic = traffic / world
         k3ms = float(t3.item())
-        nts = counts["trimers_shard"]
-        achieved = nts * mb.FLOP_PER_TRIMER / (k3ms * 1e-3) * 1e-12
+        achieved = float(nts.item()) * mb.FLOP_PER_TRIMER / (k3ms * 1e-3) * 1e-12
         step_flops = (nd * mb.FLOP_PER_DIMER + nt * mb.FLOP_PER_TRIMER)
         line = {"metric": METRIC, "value": nt / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(box, args, nd, nt),
                 "e2e": {"value": nt / float(t_e2e.item()), "unit": UNIT, "ms_per_step": 1e3 * float(t_e2e.item()),
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": "mbpol_b200_forces with pinned host arrays; per rank: H2D of coordinates + velocities, step, D2H + '+=' of "
+                                "this rank's slice of the reduced per-atom arrays"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": "k_trimers", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": traffic, "kernel_ms": k3ms,
-                             "peak_source": "measured live: independent DFMA chains (mbpol_b200_measure_fp64_peak); "
-                                            "MEASURED_PEAKS.json has no FP64 entry",
+                             "peak_source": "measured live: independent DFMA chains (mbpol_b200_measure_fp64_peak) at the SM clock in "
+                                            "`clocks`; MEASURED_PEAKS.json has no FP64 entry",
                              "algorithmic_flop_per_trimer": mb.FLOP_PER_TRIMER,
                              "step_frac": step_flops / (ms_step * 1e-3) * 1e-12 / peak / world},
-                "phases_ms": {k: float(np.mean([q[k] for q in k3])) for k in ("lists_ms", "k2b_ms", "k3b_ms", "total_ms")},
+                "phases_ms": {k: float(np.mean([q[k] for q in k3])) for k in k3[0]},
                 "clocks": clocks}
+        check = {"eng2": res["eng2"], "eng3": res["eng3"]}
         if world == 1 and not args.no_cpu_baseline:
+            # the CPU leg: the reference's own evaluator objects (oracle/_ref) under the restated list-driven driver, on ALL trimers and
+            # dimers of this box with every host thread -- it is the cpu_baseline AND the checker of the e2e result above
+            from oracle.oracle import Oracle
+            o = Oracle()
             threads = os.cpu_count() or 1
-            t, st, info = reference_sample(box, threads, args.cpu_sample or 2000 * threads)
-            line["cpu_baseline"] = {"value": st / t, "unit": UNIT, "cores": threads, "kind": info["kind"],
-                                    "sample": "%d trimers + proportional dimers of the same box, lists excluded" % st,
-                                    "flags": info["flags"], "us_per_trimer_per_thread": info["us_per_trimer_per_thread"],
-                                    "us_per_dimer_per_thread": info["us_per_dimer_per_thread"]}
-        # sanity: the summed energies of the e2e call (host accumulate semantics) stay finite
-        line["check"] = {"eng2": res["eng2"], "eng3": res["eng3"]}
+            t0 = time.perf_counter()
+            ref = o.forces(box, mode="listed", use_ref=o.have_reference, nthreads=threads, want_stress=want_s, want_fdecomp=want_w)
+            t_cpu = time.perf_counter() - t0
+            tm = ref["timing"]
+            t_eval = tm["t2b_s"] + tm["t3b_s"]
+            line["cpu_baseline"] = {"value": ref["ntrimer"] / t_eval, "unit": UNIT, "cores": threads,
+                                    "kind": "reference" if o.have_reference else "port",
+                                    "sample": "the whole box: %d dimers + %d trimers (%.2f s of evaluator time, list build %.2f s excluded)"
+                                              % (ref["ndimer"], ref["ntrimer"], t_eval, tm["list_s"]),
+                                    "flags": o.ref_flags() or "restated evaluators, g++ -O2 -ffp-contract=off", "run_flags": args.flags,
+                                    "us_per_trimer_per_thread": 1e6 * tm["t3b_s"] * threads / max(ref["ntrimer"], 1),
+                                    "us_per_dimer_per_thread": 1e6 * tm["t2b_s"] * threads / max(ref["ndimer"], 1),
+                                    "wall_s": t_cpu}
+            # the reference's real enumeration is O(N^3) (mbpol.f90:306-374): time the faithful mode at BASELINE config 1 (256 H2O)
+            b256 = synth.make_water_box(256)
+            t0 = time.perf_counter()
+            f256 = o.forces(b256, mode="faithful", use_ref=o.have_reference, nthreads=1, want_stress=want_s, want_fdecomp=want_w)
+            t256 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            o.forces(b256, mode="listed", use_ref=o.have_reference, nthreads=1, want_stress=want_s, want_fdecomp=want_w)
+            t256l = time.perf_counter() - t0
+            enum_s = max(t256 - t256l, 0.0)
+            line["cpu_baseline"]["faithful_256"] = {
+                "s_per_step_1_thread": t256, "list_driven_s_per_step_1_thread": t256l, "enumeration_s": enum_s, "n_trimers": f256["ntrimer"],
+                "triple_tests": 256 * 255 * 254 // 6,
+                "extrapolated_enumeration_s_this_box_1_thread": enum_s * (box["nw"] / 256.0) ** 3,
+                "note": "BASELINE config 1 (256 H2O): the reference driver's own O(N^3) triple loop (mbpol.f90:306-374, oracle faithful mode) "
+                        "against the list-driven mode on one thread; their difference is the enumeration cost, and its N^3 scaling to this "
+                        "box is an EXTRAPOLATION, not a measurement"}
+            e_gpu, e_ref = acc[-4] + acc[-3], ref["eng2"] + ref["eng3"]
+            k = args.steps
+            rr = lambda x, y: float(np.sqrt(np.mean((x / k - y) ** 2) / np.mean(y ** 2)))
+            e_gpu = res["eng2"] + res["eng3"]       # scalars are returned per call (fresh zero accumulators), arrays accumulate over k steps
+            check.update({"rel_err": abs(e_gpu - e_ref) / abs(e_ref), "force_rel_rms": rr(acc[:3 * n], np.concatenate([ref["fxx"], ref["fyy"], ref["fzz"]])),
+                          "against": "oracle listed mode with the reference evaluator objects, whole box, outside the timed region",
+                          "n_trimers_equal": int(ref["ntrimer"]) == int(nt), "n_dimers_equal": int(ref["ndimer"]) == int(nd)})
+        line["check"] = check
         print(json.dumps(line))
     mb.mbpol_fini(h)
     if world > 1:

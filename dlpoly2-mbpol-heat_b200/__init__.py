@@ -52,6 +52,12 @@ def load_library():
         for name in ("mbpol_b200_fini", "mbpol_b200_compute", "mbpol_b200_last_error", "mbpol_b200_stream"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.mbpol_b200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.mbpol_b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.mbpol_b200_comm_mode.argtypes = [C.c_void_p, C.c_int]
+        lib.mbpol_b200_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.mbpol_b200_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mbpol_b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        lib.mbpol_b200_host_unregister.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -114,7 +120,7 @@ def mbpol_forces_batched(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, fxx, fy
     rc = load_library().mbpol_b200_forces_batched(
         h.ptr, C.c_int(nb), C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32), C.c_int(mxatms),
         _p(xxx), _p(yyy), _p(zzz), _p(fxx), _p(fyy), _p(fzz), _p(sc[0]), _p(sc[1]), _p(sc[2]), _p(sc[3]), _p(stress),
-        _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz), _p(jflux))
+        _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz), _p(jflux if vxx is not None else None))
     _check(h, rc, "mbpol_b200_forces_batched")
     return {"eng2": sc[0], "vir2": sc[1], "eng3": sc[2], "vir3": sc[3], "stress": stress, "jflux": jflux}
 
@@ -130,6 +136,77 @@ def mbpol_set_shard(h, rank, nranks):
     _check(h, load_library().mbpol_b200_set_shard(h.ptr, int(rank), int(nranks)), "mbpol_b200_set_shard")
 
 
+# ---- multi-GPU: NCCL inside the library (include/mbpol_b200.h) --------------------------------------------------------
+UNIQUE_ID_BYTES = 128
+
+
+def mbpol_comm_unique_id():
+    """ncclGetUniqueId through the library: call on ONE rank and ship the bytes to the others (MPI_Bcast, torch.distributed, ...)."""
+    buf = (C.c_ubyte * UNIQUE_ID_BYTES)()
+    rc = load_library().mbpol_b200_comm_unique_id(buf)
+    if rc:
+        raise MBPolError("mbpol_b200_comm_unique_id failed with status %d" % rc)
+    return bytes(buf)
+
+
+def mbpol_comm_init(h, rank, nranks, uid):
+    """The handle joins the communicator (and takes shard `rank` of `nranks`); every later step ends with the in-library reduction."""
+    assert len(uid) == UNIQUE_ID_BYTES
+    buf = (C.c_ubyte * UNIQUE_ID_BYTES).from_buffer_copy(uid)
+    _check(h, load_library().mbpol_b200_comm_init(h.ptr, C.c_int(int(rank)), C.c_int(int(nranks)), buf), "mbpol_b200_comm_init")
+
+
+def mbpol_comm_mode(h, mode):
+    """0 no reduction, 1 all-reduce, 2 reduce-scatter (default with a communicator): rank r returns slice r of the per-atom arrays."""
+    _check(h, load_library().mbpol_b200_comm_mode(h.ptr, C.c_int(int(mode))), "mbpol_b200_comm_mode")
+
+
+def shard_bounds(nw, nranks, weight=None):
+    """Water ranges of the ranks: bounds[r] .. bounds[r+1] (uniform, or balanced on the previous step's per-water weights)."""
+    b = np.zeros(nranks + 1, dtype=np.int32)
+    wp = None
+    if weight is not None:
+        weight = np.ascontiguousarray(weight, dtype=np.int32)
+        assert len(weight) == nw
+        wp = weight.ctypes.data_as(_ip)
+    lib = load_library()
+    lib.mbpol_b200_shard_bounds.restype = None
+    lib.mbpol_b200_shard_bounds(C.c_int(int(nw)), C.c_int(int(nranks)), wp, b.ctypes.data_as(_ip))
+    return b
+
+
+def packed_layout(mxatms, nranks, nbeads=1):
+    """Host mirror of the packed device buffer: (chunk, scalar offset, total count).  The per-atom part [fxx|fyy|fzz|e|S(9)|W(9)]
+    of 22*mxatms doubles is padded to nranks equal even chunks (the unit of the reduce-scatter), then 32 scalars per bead."""
+    chunk = (22 * mxatms + nranks - 1) // nranks
+    chunk += chunk & 1
+    return chunk, chunk * nranks, chunk * nranks + 32 * nbeads
+
+
+def mbpol_shard(h):
+    a, b, o = C.c_int(), C.c_int(), C.c_longlong()
+    _check(h, load_library().mbpol_b200_shard(h.ptr, C.byref(a), C.byref(b), C.byref(o)), "mbpol_b200_shard")
+    return {"first_water": a.value, "n_waters": b.value, "scalar_offset": o.value}
+
+
+def mbpol_phase_times(h):
+    ms = (C.c_float * 8)()
+    _check(h, load_library().mbpol_b200_phase_times(h.ptr, ms, C.c_int(8)), "mbpol_b200_phase_times")
+    keys = ("lists_ms", "k2b_ms", "k3b_ms", "total_ms", "k_trimers_ms", "gather_ms", "reduce_ms", "incidence_ms")
+    return {k: float(ms[i]) for i, k in enumerate(keys)}
+
+
+def host_register(a):
+    """Pin a caller array once (cudaHostRegister) so that the per-step copies run at PCIe speed."""
+    rc = load_library().mbpol_b200_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes))
+    if rc:
+        raise MBPolError("mbpol_b200_host_register failed with status %d" % rc)
+
+
+def host_unregister(a):
+    load_library().mbpol_b200_host_unregister(C.c_void_p(a.ctypes.data))
+
+
 def mbpol_forces(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, fxx, fyy, fzz, engsrp=0.0, virsrp=0.0, stress=None,
                  atomic_energy=None, atomic_stress=None, atomic_fdecomp=None, vxx=None, vyy=None, vzz=None):
     """The drop-in for mbpol_forces (mbpol.f90:98-449): accumulates into fxx/fyy/fzz/stress and the per-atom arrays
@@ -143,7 +220,8 @@ def mbpol_forces(h, imcon, cell, nttm2, listttm2, xxx, yyy, zzz, fxx, fyy, fzz, 
     rc = lib.mbpol_b200_forces(h.ptr, C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32),
                                C.c_int(len(xxx)), _p(xxx), _p(yyy), _p(zzz), _p(fxx), _p(fyy), _p(fzz),
                                C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]), C.byref(sc[3]), _p(stress),
-                               _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz), _p(jflux))
+                               _p(atomic_energy), _p(atomic_stress), _p(atomic_fdecomp), _p(vxx), _p(vyy), _p(vzz),
+                               _p(jflux if vxx is not None else None))
     _check(h, rc, "mbpol_b200_forces")
     eng2, vir2, eng3, vir3 = (s.value for s in sc)
     return {"eng2": eng2, "vir2": vir2, "eng3": eng3, "vir3": vir3, "engsrp": engsrp + eng2 + eng3,
@@ -192,12 +270,14 @@ def mbpol_counts(h):
 
 
 def mbpol_lists(h):
+    """This rank's shard of the dimer / trimer lists (the whole lists on a single rank), 0-based water indices."""
     c = mbpol_counts(h)
-    d = np.zeros((max(c["dimers"], 1), 2), dtype=np.int32)
-    t = np.zeros((max(c["trimers"], 1), 3), dtype=np.int32)
-    rc = load_library().mbpol_b200_get_lists(h.ptr, _p(d, np.int32), C.c_longlong(c["dimers"]), _p(t, np.int32), C.c_longlong(c["trimers"]))
+    nd, nt = c["dimers_shard"], c["trimers_shard"]
+    d = np.zeros((max(nd, 1), 2), dtype=np.int32)
+    t = np.zeros((max(nt, 1), 3), dtype=np.int32)
+    rc = load_library().mbpol_b200_get_lists(h.ptr, _p(d, np.int32), C.c_longlong(nd), _p(t, np.int32), C.c_longlong(nt))
     _check(h, rc, "mbpol_b200_get_lists")
-    return d[:c["dimers"]], t[:c["trimers"]]
+    return d[:nd], t[:nt]
 
 
 def mbpol_kernel_times(h):

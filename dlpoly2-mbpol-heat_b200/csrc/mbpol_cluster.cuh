@@ -14,7 +14,7 @@ namespace mbpol_k {
 constexpr int NB2_CAP = 96;    // neighbours j>i within r2f (6.5 A): ~19 on average in liquid water
 constexpr int NB3_CAP = 40;    // neighbours within r3f (4.5 A): ~13 on average
 constexpr int NSCAL = 32;
-enum { S_ENG2 = 0, S_VIR2 = 1, S_ENG3 = 2, S_VIR3 = 3, S_STRESS = 4, S_JFLUX = 13, S_ND = 22, S_NT = 23 };
+enum { S_ENG2 = 0, S_VIR2 = 1, S_ENG3 = 2, S_VIR3 = 3, S_STRESS = 4, S_JFLUX = 13, S_ND = 22, S_NT = 23, S_OVF = 24 };
 
 struct OutPtrs {      // views into the packed output buffer
     double *fx, *fy, *fz, *aeng, *astress, *afd, *scal;
@@ -132,14 +132,15 @@ __device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict
 
 template <int ENGINE>
 __global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
-k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __restrict__ mono, CellInfo C,
+k_trimers(const long long* __restrict__ pcount, const int* __restrict__ tri, int nw, const double* __restrict__ mono, CellInfo C,
           const double* __restrict__ tape, double* __restrict__ rec)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const long long first = (long long)blockIdx.x * blockDim.x;
+    const long long ntri = *pcount;          // written on the device by the list build: no host round trip before the launch
+    const PolyCtx ctx{dyn_smem, tape};
+    for (long long first = (long long)blockIdx.x * blockDim.x; first < ntri; first += (long long)gridDim.x * blockDim.x) {
     const long long t0_ = first + threadIdx.x;
     const long long t = t0_ < ntri ? t0_ : ntri - 1;     // idle lanes shadow the last trimer: the tape walk has CTA barriers
-    const PolyCtx ctx{dyn_smem, tape};
     double out[MBPOL_REC3];
     {
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
@@ -161,6 +162,8 @@ k_trimers(long long ntri, const int* __restrict__ tri, int nw, const double* __r
     for (int i = threadIdx.x; i < nvalid * (MBPOL_REC3 / 2); i += blockDim.x) {
         const int tr = i / (MBPOL_REC3 / 2), pr = i % (MBPOL_REC3 / 2);
         dst[i] = *reinterpret_cast<const double2*>(stage + tr * MBPOL_REC3_STRIDE + 2 * pr);
+    }
+    __syncthreads();      // the staged records are out before the next tile overwrites the columns
     }
 }
 
@@ -317,17 +320,19 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
 }
 
 // incidence lists: water -> (trimer << 2 | slot) for the trimers [0, ntri) of this shard
-__global__ void k_inc_count(long long ntri, const int* __restrict__ tri, int* __restrict__ cnt)
+__global__ void k_inc_count(const long long* __restrict__ pcount, const int* __restrict__ tri, int* __restrict__ cnt)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 3 * ntri) atomicAdd(&cnt[tri[i]], 1);
+    const long long n3 = 3 * *pcount;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) atomicAdd(&cnt[tri[i]], 1);
 }
-__global__ void k_inc_fill(long long ntri, const int* __restrict__ tri, const int* __restrict__ off, int* __restrict__ cur, unsigned* __restrict__ inc)
+__global__ void k_inc_fill(const long long* __restrict__ pcount, const int* __restrict__ tri, const int* __restrict__ off, int* __restrict__ cur,
+                           unsigned* __restrict__ inc)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * ntri) return;
-    const int w = tri[i];
-    inc[off[w] + atomicAdd(&cur[w], 1)] = (unsigned)((i / 3) << 2) | (unsigned)(i % 3);
+    const long long n3 = 3 * *pcount;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
+        const int w = tri[i];
+        inc[off[w] + atomicAdd(&cur[w], 1)] = (unsigned)((i / 3) << 2) | (unsigned)(i % 3);
+    }
 }
 
 #endif   // MBPOL_GATHER_KERNELS
@@ -337,12 +342,14 @@ __global__ void k_inc_fill(long long ntri, const int* __restrict__ tri, const in
 // ---------------------------------------------------------------------------------------------------------
 template <int ENGINE>
 __global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
-k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
+k_dimers(const long long* __restrict__ pcount, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
          const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
          const double* __restrict__ tape)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    const long long t0_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ndim = *pcount;
+    for (long long first = (long long)blockIdx.x * blockDim.x; first < ndim; first += (long long)gridDim.x * blockDim.x) {
+    const long long t0_ = first + threadIdx.x;
     bool valid = t0_ < ndim;
     const long long t = valid ? t0_ : ndim - 1;
     const PolyCtx ctx{dyn_smem, tape};
@@ -428,6 +435,7 @@ k_dimers(long long ndim, const int2* __restrict__ dim, int nw, const double* __r
     block_reduce_add_bead<2>(v2, O.scal, S_ENG2, bead);
     double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
     block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

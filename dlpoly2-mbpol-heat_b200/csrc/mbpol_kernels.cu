@@ -11,6 +11,7 @@
 // Scatter: FP64 red.global.add into the packed output buffer; scalars are block-reduced first.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -49,11 +50,11 @@ using namespace mbpol_k;
 
 // the (kernel, engine) instantiations live in mbpol_inst.cu
 namespace mbpol_k {
-extern template __global__ void k_dimers<1>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_dimers<3>(long long, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_trimers<1>(long long, const int*, int, const double*, CellInfo, const double*, double*);
-extern template __global__ void k_trimers<3>(long long, const int*, int, const double*, CellInfo, const double*, double*);
-extern template __global__ void k_trimers<4>(long long, const int*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_dimers<1>(const long long*, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_dimers<3>(const long long*, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_trimers<1>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_trimers<3>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_trimers<4>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
 extern template __global__ void k_eval_dimers<1>(int, const double*, double*, double*, double*, const double*);
 extern template __global__ void k_eval_dimers<3>(int, const double*, double*, double*, double*, const double*);
 extern template __global__ void k_eval_trimers<1>(int, const double*, double*, double*, double*, const double*);
@@ -126,7 +127,7 @@ __global__ void k_cell_fill(int nw, const int* __restrict__ cell_id, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1b: neighbour rows.  Thread per water i (taken in cell order so a warp works on one neighbourhood).
+// K1b: neighbour rows of the owned waters.
 //   nb2[i][*]: j > i with  r^2 <= r2f^2     (reject: r^2 .gt. r2f**2, mbpol.f90:502)
 //   nb3[i][*]: j != i with sqrt(r^2) <= r3f (reject: r .gt. r3f,      mbpol.f90:865-869)
 // d = O_min(i,j) - O_max(i,j), then the reference's minimum image.
@@ -147,16 +148,18 @@ __global__ void k_sort_cells(int ncells, const int* __restrict__ cell_start, int
     }
 }
 
-// One WARP per water: the lanes share the scan of the 27 surrounding cells; accepted partners are appended with a
-// ballot/prefix so the row order is (cell order, member order) -- deterministic.
-__global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C, Grid G, const int* __restrict__ cell_start,
+// One WARP per water of this rank's range [w0, w0 + nown): the lanes share the scan of the 27 surrounding cells; accepted
+// partners are appended with a ballot/prefix so the row order is (cell order, member order) -- deterministic.  Rows are
+// indexed by the LOCAL water number i - w0: every rank builds only the rows of the waters it owns (mbpol.f90:218-226, 311-314
+// split the pair / triple loops over the ranks of a bead in the same spirit).
+__global__ void k_neighbours(int w0, int nown, int nw, const double* __restrict__ mono, CellInfo C, Grid G, const int* __restrict__ cell_start,
                              const int* __restrict__ sorted, int* __restrict__ nb2, int* __restrict__ n2, int* __restrict__ nb3,
                              int* __restrict__ n3, int* __restrict__ overflow)
 {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    if (t >= nw) return;
-    const int i = sorted[t];
+    if (t >= nown) return;
+    const int i = w0 + t;
     const double xi = mono[i], yi = mono[(size_t)nw + i], zi = mono[2 * (size_t)nw + i];
     int ci[3];
     cell_of(G, xi, yi, zi, ci);
@@ -193,50 +196,62 @@ __global__ void k_neighbours(int nw, const double* __restrict__ mono, CellInfo C
                     }
                     const unsigned b2 = __ballot_sync(0xffffffffu, in2), b3 = __ballot_sync(0xffffffffu, in3);
                     const int q2 = c2 + __popc(b2 & lt), q3 = c3 + __popc(b3 & lt);
-                    if (in2 && q2 < NB2_CAP) nb2[(size_t)i * NB2_CAP + q2] = j;
-                    if (in3 && q3 < NB3_CAP) nb3[(size_t)i * NB3_CAP + q3] = j;
+                    if (in2 && q2 < NB2_CAP) nb2[(size_t)t * NB2_CAP + q2] = j;
+                    if (in3 && q3 < NB3_CAP) nb3[(size_t)t * NB3_CAP + q3] = j;
                     c2 += __popc(b2);
                     c3 += __popc(b3);
                 }
             }
     if (lane == 0) {
         if (c2 > NB2_CAP || c3 > NB3_CAP) atomicExch(overflow, 1);
-        n2[i] = min(c2, NB2_CAP);
-        n3[i] = min(c3, NB3_CAP);
+        n2[t] = min(c2, NB2_CAP);
+        n3[t] = min(c3, NB3_CAP);
     }
 }
 
-__global__ void k_fill_dimers(int nw, const int* __restrict__ nb2, const int* __restrict__ n2, const long long* __restrict__ off,
-                              int2* __restrict__ dimers)
+__global__ void k_fill_dimers(int w0, int nown, const int* __restrict__ nb2, const int* __restrict__ n2, const long long* __restrict__ off,
+                              int2* __restrict__ dimers, long long cap, int* __restrict__ overflow)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nw) return;
-    const long long o = off[i];
-    for (int q = 0; q < n2[i]; ++q) dimers[o + q] = make_int2(i, nb2[(size_t)i * NB2_CAP + q]);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nown) return;
+    const long long o = off[t];
+    if (o + n2[t] > cap) { atomicExch(overflow, 2); return; }
+    for (int q = 0; q < n2[t]; ++q) dimers[o + q] = make_int2(w0 + t, nb2[(size_t)t * NB2_CAP + q]);
+}
+
+// the 3B list predicate for one pair, with the reference's arithmetic (d = O_min - O_max, minimum image, r .gt. r3f rejects:
+// mbpol.f90:843-869) -- the same bits k_neighbours computes, so a rank needs no neighbour rows of waters it does not own
+__device__ __forceinline__ bool within_r3f(int nw, const double* __restrict__ mono, const CellInfo& C, int a, int b)
+{
+    const int i = min(a, b), j = max(a, b);
+    double dx = __dsub_rn(mono[i], mono[j]), dy = __dsub_rn(mono[(size_t)nw + i], mono[(size_t)nw + j]),
+           dz = __dsub_rn(mono[2 * (size_t)nw + i], mono[2 * (size_t)nw + j]);
+    image_vec(C, dx, dy, dz);
+    return !(__dsqrt_rn(norm2_exact(dx, dy, dz)) > mbpol_par.r3f);
 }
 
 // A triple is accepted iff at least two of its three O-O distances are <= r3f (mbpol.f90:865-869).  Enumerate it from
 // a centre c that is within r3f of both others; when all three pairs are close every water is such a centre and the
-// triple is emitted from the smallest index only.
-__device__ __forceinline__ bool in_row(const int* __restrict__ row, int n, int v)
-{
-    for (int q = 0; q < n; ++q)
-        if (row[q] == v) return true;
-    return false;
-}
-
+// triple is emitted from the smallest index only.  One warp per owned centre.  The count pass also leaves the centre's
+// load-balancing weight (4 x trimers + dimers) for the next step's shard boundaries.
 template <bool FILL>
-__global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* __restrict__ n3, long long* __restrict__ cnt,
-                               const long long* __restrict__ off, int* __restrict__ trimers)
+__global__ void k_trimers_enum(int w0, int nown, int nw, const double* __restrict__ mono, CellInfo C, const int* __restrict__ nb3,
+                               const int* __restrict__ n3, const int* __restrict__ n2, long long* __restrict__ cnt, int* __restrict__ weight,
+                               const long long* __restrict__ off, int* __restrict__ trimers, long long cap, int* __restrict__ overflow)
 {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per centre
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per centre
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    if (c >= nw) return;
-    const int* row = nb3 + (size_t)c * NB3_CAP;
-    const int n = n3[c];
+    if (t >= nown) return;
+    const int c = w0 + t;
+    const int* row = nb3 + (size_t)t * NB3_CAP;
+    const int n = n3[t];
     const int npairs = n * (n - 1) / 2;
     long long k = 0;
-    const long long base = FILL ? off[c] : 0;
+    const long long base = FILL ? off[t] : 0;
+    if (FILL && base + (off[t + 1] - base) > cap) {
+        if (lane == 0) atomicExch(overflow, 3);
+        return;
+    }
     for (int e0 = 0; e0 < npairs; e0 += 32) {
         const int e = e0 + (int)lane;
         bool emit = false;
@@ -249,7 +264,7 @@ __global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* _
             const int pp = e - q * (q - 1) / 2;
             a = row[pp];
             b = row[q];
-            const bool closed = in_row(nb3 + (size_t)a * NB3_CAP, n3[a], b);
+            const bool closed = within_r3f(nw, mono, C, a, b);
             emit = !(closed && !(c < a && c < b));
         }
         const unsigned m = __ballot_sync(0xffffffffu, emit);
@@ -263,7 +278,25 @@ __global__ void k_trimers_enum(int nw, const int* __restrict__ nb3, const int* _
         }
         k += __popc(m);
     }
-    if (!FILL && lane == 0) cnt[c] = k;
+    if (!FILL && lane == 0) {
+        cnt[t] = k;
+        weight[c] = (int)(4 * k) + n2[t];
+    }
+}
+
+// shard totals -> the scalar block (slots S_ND / S_NT of bead 0: they ride through the reduction, so every rank learns the
+// box totals) and the device-side counts the evaluation kernels loop over
+__global__ void k_publish_counts(const long long* __restrict__ off2_end, const long long* __restrict__ off3_end, long long cap2, long long cap3,
+                                 long long grid2, long long grid3, long long* __restrict__ counts, double* __restrict__ scal)
+{
+    const long long nd = min(*off2_end, cap2), nt = min(*off3_end, cap3);
+    counts[0] = nd; counts[1] = nt;
+    counts[2] = *off2_end; counts[3] = *off3_end;
+    scal[S_ND] += (double)nd;
+    scal[S_NT] += (double)nt;
+    // a list that does not fit its estimated capacity (or has no launch at all) makes EVERY rank repeat the step: the mark
+    // travels through the all-reduce of the scalar block
+    if (*off2_end > cap2 || *off3_end > cap3 || (*off2_end > 0 && grid2 <= 0) || (*off3_end > 0 && grid3 <= 0)) scal[S_OVF] += 1.0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -488,30 +521,41 @@ struct mbpol_b200_handle {
     bool have_vel = false, uploaded = false;
     std::string err;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CellInfo C;
     Grid G;
     int ncells = 0;
     DevBuf<double> xyz, vel, mono, out, rec;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
-    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur;
+    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur, weight;
     DevBuf<unsigned> inc;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
-    DevBuf<long long> off2, off3, cnt3, n2ll;
+    DevBuf<long long> off2, off3, cnt3, n2ll, counts;
     DevBuf<char> scan_tmp;
-    std::vector<double> host_out;
     std::vector<int> host_list;
     double* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<cudaEvent_t> dl_ev;            // one event behind every piece of the pipelined download
+    // shard of this rank: the waters [w0, w0 + nown) are its centres (trimers) / first members (dimers)
+    int w0 = 0, nown = 0;
+    long long est_nd = -1, est_nt = -1;        // counts of the previous step: sizes and grids of this one (no host round trip)
+    struct HostBack { long long counts[4]; double tail[3]; int flag; int pad; } *back = nullptr;     // pinned: read back once per step
+    int* host_weight = nullptr;                // pinned: per-water load-balancing weights of the previous step (all ranks)
+    bool have_weight = false;
+    ncclComm_t comm = nullptr;
+    int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
-    float ms[4] = {0, 0, 0, 0};
-    size_t out_count() const { return (size_t)22 * mxatms + (size_t)NSCAL * nbeads; }
+    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // packed output buffer: [22 per-atom arrays of mxatms | pad to nranks equal chunks | NSCAL scalars per bead]
+    size_t atom_count() const { return (size_t)22 * mxatms; }
+    size_t chunk() const { const size_t c = (atom_count() + nranks - 1) / nranks; return (c + 1) & ~(size_t)1; }
+    size_t scal_offset() const { return chunk() * nranks; }
+    size_t out_count() const { return scal_offset() + (size_t)NSCAL * nbeads; }
     OutPtrs views()
     {
         OutPtrs O;
         const size_t n = mxatms;
         O.fx = out.p; O.fy = out.p + n; O.fz = out.p + 2 * n; O.aeng = out.p + 3 * n;
-        O.astress = out.p + 4 * n; O.afd = out.p + 13 * n; O.scal = out.p + 22 * n; O.mxatms = mxatms; O.nwb = nwb; O.mxb = mxb;
+        O.astress = out.p + 4 * n; O.afd = out.p + 13 * n; O.scal = out.p + scal_offset(); O.mxatms = mxatms; O.nwb = nwb; O.mxb = mxb;
         return O;
     }
 };
@@ -539,7 +583,39 @@ int scan_int(mbpol_b200_handle* h, const int* in, int* out, int n)
     CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, bytes, in, out, n, h->stream));
     return 0;
 }
+
+#define NCCL_TRY(h, call)                                                                                   \
+    do {                                                                                                    \
+        ncclResult_t r_ = (call);                                                                           \
+        if (r_ != ncclSuccess) {                                                                            \
+            (h)->err = std::string(#call) + ": " + ncclGetErrorString(r_);                                  \
+            return MBPOL_B200_ECUDA;                                                                        \
+        }                                                                                                   \
+    } while (0)
 }  // namespace
+
+// Shard boundaries: the waters are cut into nranks contiguous ranges of (nearly) equal WEIGHT, weight = 4 x trimers + dimers a
+// water owned in the previous step; without weights (first step, one rank) the cut is uniform.
+// Pure host arithmetic on data every rank holds identically -- exposed for the CPU tests.
+extern "C" void mbpol_b200_shard_bounds(int nw, int nranks, const int* weight /* nw or NULL */, int* bounds /* nranks + 1 */)
+{
+    bounds[0] = 0;
+    long long total = 0;
+    if (weight)
+        for (int i = 0; i < nw; ++i) total += weight[i] > 0 ? weight[i] : 0;
+    if (!weight || total <= 0) {
+        for (int r = 1; r <= nranks; ++r) bounds[r] = (int)((long long)nw * r / nranks);
+        return;
+    }
+    long long acc = 0;
+    int r = 1;
+    for (int i = 0; i < nw && r < nranks; ++i) {
+        acc += weight[i] > 0 ? weight[i] : 0;
+        while (r < nranks && acc * nranks >= total * r) bounds[r++] = i + 1;
+    }
+    for (; r <= nranks; ++r) bounds[r] = nw;
+    bounds[nranks] = nw;
+}
 
 extern "C" {
 
@@ -569,6 +645,7 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
+    if (cudaMallocHost(&h->back, sizeof(*h->back)) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     *handle = h;
     return MBPOL_B200_OK;
 }
@@ -578,8 +655,11 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     if (!h) return MBPOL_B200_EINVAL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->comm) ncclCommDestroy(h->comm);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->back) cudaFreeHost(h->back);
+    if (h->host_weight) cudaFreeHost(h->host_weight);
     for (cudaEvent_t e : h->dl_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -593,9 +673,42 @@ void mbpol_b200_cutoffs(double* r2f, double* r3f) { *r2f = MBPOL_P2b_r2f; *r3f =
 int mbpol_b200_set_shard(mbpol_b200_handle* h, int rank, int nranks)
 {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks) return MBPOL_B200_EINVAL;
+    if (h->comm && (rank != h->rank || nranks != h->nranks)) { h->err = "the shard of a handle with a communicator is fixed by mbpol_b200_comm_init"; return MBPOL_B200_EINVAL; }
+    if (rank != h->rank || nranks != h->nranks) { h->est_nd = h->est_nt = -1; h->have_weight = false; }
     h->rank = rank; h->nranks = nranks;
     return MBPOL_B200_OK;
 }
+
+// ---- NCCL inside the boundary: the handle owns the communicator, the reduction runs on the handle's stream --------------
+int mbpol_b200_comm_unique_id(void* id)
+{
+    static_assert(sizeof(ncclUniqueId) == MBPOL_B200_UNIQUE_ID_BYTES, "NCCL unique id size");
+    if (!id) return MBPOL_B200_EINVAL;
+    return ncclGetUniqueId(reinterpret_cast<ncclUniqueId*>(id)) == ncclSuccess ? MBPOL_B200_OK : MBPOL_B200_ECUDA;
+}
+
+int mbpol_b200_comm_init(mbpol_b200_handle* h, int rank, int nranks, const void* id)
+{
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks || h->comm) return MBPOL_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(h, ncclCommInitRank(&h->comm, nranks, uid, rank));
+    h->rank = rank; h->nranks = nranks;
+    h->est_nd = h->est_nt = -1; h->have_weight = false;
+    h->reduce_mode = nranks > 1 ? 2 : 0;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_comm_mode(mbpol_b200_handle* h, int mode)
+{
+    if (!h || mode < 0 || mode > 2 || (mode && !h->comm)) return MBPOL_B200_EINVAL;
+    h->reduce_mode = h->nranks > 1 ? mode : 0;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_host_register(void* p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? MBPOL_B200_OK : MBPOL_B200_ECUDA; }
+int mbpol_b200_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? MBPOL_B200_OK : MBPOL_B200_ECUDA; }
 
 void* mbpol_b200_stream(mbpol_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
 
@@ -607,6 +720,11 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
         h->err = "mbpol_b200_upload: invalid argument (imcon must be 1, 2 or 3; nttm2 must match init)";
         return MBPOL_B200_EINVAL;
     }
+    for (int t = 0; t < nttm2; t += 3)      // H atoms are addressed as o+1, o+2 (mbpol.f90:526-527, 592-594): the whole water must be in range
+        if (listttm2[t] < 1 || listttm2[t] + 2 > mxatms || listttm2[t + 1] < 1 || listttm2[t + 1] > mxatms || listttm2[t + 2] < 1 || listttm2[t + 2] > mxatms) {
+            h->err = "mbpol_b200_upload: listttm2 entry out of range [1, mxatms]";
+            return MBPOL_B200_EINVAL;
+        }
     CUDA_TRY(h, cudaSetDevice(h->device));
     // bead-batched handles: the arrays hold nbeads consecutive systems of mxatms atoms (one bead otherwise)
     h->mxb = mxatms;
@@ -665,29 +783,43 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
     return MBPOL_B200_OK;
 }
 
-int mbpol_b200_compute(mbpol_b200_handle* h)
+// One step on the handle's stream.  With counts from the previous step at hand (est_nd / est_nt) nothing between the first
+// and the last launch waits for the host: list capacities and grids come from the estimates, the kernels read the true counts
+// from device memory, and an overflow flag (checked after the single synchronisation at the end) triggers a sized retry.
+static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
 {
-    if (!h || !h->uploaded) return MBPOL_B200_EINVAL;
-    CUDA_TRY(h, cudaSetDevice(h->device));
     const int nw = h->nw;
     const size_t n = h->mxatms;
     cudaStream_t s = h->stream;
-    const int TB = 128, gb = (nw + TB - 1) / TB;
+    const int TB = 128;
     h->launches = 0;
+    // shard of this rank
+    {
+        std::vector<int> bounds(h->nranks + 1);
+        mbpol_b200_shard_bounds(nw, h->nranks, (h->nranks > 1 && h->have_weight) ? h->host_weight : nullptr, bounds.data());
+        h->w0 = bounds[h->rank];
+        h->nown = bounds[h->rank + 1] - bounds[h->rank];
+    }
+    const int w0 = h->w0, nown = h->nown;
+    const int gb = (nw + TB - 1) / TB, go = (nown + TB - 1) / TB;
     CUDA_TRY(h, h->mono.reserve(9 * (size_t)nw));
     CUDA_TRY(h, h->out.reserve(h->out_count()));
     CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw));
     CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
-    CUDA_TRY(h, h->nb2.reserve((size_t)nw * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)nw * NB3_CAP));
-    CUDA_TRY(h, h->n2.reserve(nw)); CUDA_TRY(h, h->n3.reserve(nw)); CUDA_TRY(h, h->flag.reserve(1));
-    CUDA_TRY(h, h->off2.reserve(nw + 1)); CUDA_TRY(h, h->off3.reserve(nw + 1)); CUDA_TRY(h, h->cnt3.reserve(nw + 1));
-    CUDA_TRY(h, h->n2ll.reserve(nw + 1));
+    CUDA_TRY(h, h->nb2.reserve((size_t)std::max(nown, 1) * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)std::max(nown, 1) * NB3_CAP));
+    CUDA_TRY(h, h->n2.reserve(nown + 1)); CUDA_TRY(h, h->n3.reserve(nown + 1)); CUDA_TRY(h, h->flag.reserve(1));
+    CUDA_TRY(h, h->off2.reserve(nown + 1)); CUDA_TRY(h, h->off3.reserve(nown + 1)); CUDA_TRY(h, h->cnt3.reserve(nown + 1));
+    CUDA_TRY(h, h->n2ll.reserve(nown + 1)); CUDA_TRY(h, h->counts.reserve(4)); CUDA_TRY(h, h->weight.reserve(nw + 1));
+    CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
 
     CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
     CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_count() * 8, s));
+    OutPtrs O = h->views();
+    h->back->flag = 0;
+    for (long long& c : h->back->counts) c = 0;
     if (nw == 0) {   // no water at all (the reference's loops simply do not execute): zero contributions, nothing to launch
         h->nd_total = h->nt_total = h->nd_shard = h->nt_shard = 0;
-        for (int k = 1; k < 5; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
+        for (int k = 1; k < 10; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
         CUDA_TRY(h, cudaStreamSynchronize(s));
         for (float& m : h->ms) m = 0.f;
         return MBPOL_B200_OK;
@@ -695,87 +827,146 @@ int mbpol_b200_compute(mbpol_b200_handle* h)
     CUDA_TRY(h, cudaMemsetAsync(h->cell_cnt.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->cell_fill.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->flag.p, 0, 4, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->weight.p, 0, (size_t)(nw + 1) * 4, s));
     k_gather_image<<<gb, TB, 0, s>>>(nw, h->list.p, h->xyz.p, h->xyz.p + n, h->xyz.p + 2 * n, h->C, h->mono.p);
     k_cell_index<<<gb, TB, 0, s>>>(nw, h->mono.p, h->G, h->cell_id.p, h->cell_cnt.p);
     if (int rc = scan_int(h, h->cell_cnt.p, h->cell_cnt.p, h->ncells + 1)) return rc;   // in-place exclusive scan -> cell_start
     k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->sorted.p);
     k_sort_cells<<<(h->ncells + TB - 1) / TB, TB, 0, s>>>(h->ncells, h->cell_cnt.p, h->sorted.p);
-    const int gw = (int)(((size_t)nw * 32 + TB - 1) / TB);      // one warp per water
-    k_neighbours<<<gw, TB, 0, s>>>(nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
-    k_widen<<<(nw + 1 + TB - 1) / TB, TB, 0, s>>>(nw, h->n2.p, h->n2ll.p);
-    CUDA_TRY(h, cudaMemsetAsync(h->n2ll.p + nw, 0, 8, s));
-    CUDA_TRY(h, cudaMemsetAsync(h->cnt3.p + nw, 0, 8, s));
-    if (int rc = scan_ll(h, h->n2ll.p, h->off2.p, nw + 1)) return rc;
-    k_trimers_enum<false><<<gw, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, h->cnt3.p, nullptr, nullptr);
-    if (int rc = scan_ll(h, h->cnt3.p, h->off3.p, nw + 1)) return rc;
-    h->launches += 10;
-    long long tot[2];
-    int ovf = 0;
-    CUDA_TRY(h, cudaMemcpyAsync(&tot[0], h->off2.p + nw, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaMemcpyAsync(&tot[1], h->off3.p + nw, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaMemcpyAsync(&ovf, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
-    if (ovf) { h->err = "neighbour capacity exceeded (NB2_CAP/NB3_CAP): unphysical density"; return MBPOL_B200_ECAPACITY; }
-    h->nd_total = tot[0]; h->nt_total = tot[1];
-    CUDA_TRY(h, h->dimers.reserve((size_t)std::max<long long>(tot[0], 1)));
-    CUDA_TRY(h, h->trimers.reserve((size_t)std::max<long long>(3 * tot[1], 3)));
-    k_fill_dimers<<<gb, TB, 0, s>>>(nw, h->nb2.p, h->n2.p, h->off2.p, h->dimers.p);
-    k_trimers_enum<true><<<gw, TB, 0, s>>>(nw, h->nb3.p, h->n3.p, nullptr, h->off3.p, h->trimers.p);
-    h->launches += 2;
+    h->launches += 6;
+    const int gw = (int)(((size_t)std::max(nown, 1) * 32 + TB - 1) / TB);      // one warp per owned water
+    if (nown > 0) {
+        k_neighbours<<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
+        k_widen<<<go, TB, 0, s>>>(nown, h->n2.p, h->n2ll.p);
+        k_trimers_enum<false><<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->nb3.p, h->n3.p, h->n2.p, h->cnt3.p, h->weight.p, nullptr, nullptr, 0, h->flag.p);
+        h->launches += 3;
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->n2ll.p + nown, 0, 8, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->cnt3.p + nown, 0, 8, s));
+    if (int rc = scan_ll(h, h->n2ll.p, h->off2.p, nown + 1)) return rc;
+    if (int rc = scan_ll(h, h->cnt3.p, h->off3.p, nown + 1)) return rc;
+    h->launches += 4;
+    long long cap2, cap3;
+    if (sized_by_estimate) {
+        cap2 = h->est_nd + h->est_nd / 4 + 4096;
+        cap3 = h->est_nt + h->est_nt / 4 + 4096;
+    } else {   // first step (or after an overflow): read the totals back once
+        long long tot[2];
+        int ovf = 0;
+        CUDA_TRY(h, cudaMemcpyAsync(&tot[0], h->off2.p + nown, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(&tot[1], h->off3.p + nown, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(&ovf, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        if (ovf == 1) { h->err = "neighbour capacity exceeded (NB2_CAP/NB3_CAP): unphysical density"; return MBPOL_B200_ECAPACITY; }
+        cap2 = tot[0]; cap3 = tot[1];
+        h->est_nd = tot[0]; h->est_nt = tot[1];
+    }
+    CUDA_TRY(h, h->dimers.reserve((size_t)std::max<long long>(cap2, 1)));
+    CUDA_TRY(h, h->trimers.reserve((size_t)std::max<long long>(3 * cap3, 3)));
+    CUDA_TRY(h, h->rec.reserve((size_t)std::max<long long>(cap3, 1) * MBPOL_REC3));
+    CUDA_TRY(h, h->inc.reserve((size_t)std::max<long long>(3 * cap3, 3)));
+    if (nown > 0) {
+        k_fill_dimers<<<go, TB, 0, s>>>(w0, nown, h->nb2.p, h->n2.p, h->off2.p, h->dimers.p, cap2, h->flag.p);
+        k_trimers_enum<true><<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->nb3.p, h->n3.p, h->n2.p, nullptr, nullptr, h->off3.p, h->trimers.p, cap3, h->flag.p);
+        h->launches += 2;
+    }
+    k_publish_counts<<<1, 1, 0, s>>>(h->off2.p + nown, h->off3.p + nown, cap2, cap3, h->est_nd, h->est_nt, h->counts.p, O.scal);
+    ++h->launches;
     CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
 
-    // contiguous shard of each list (the analogue of the bead_rank/bead_size stride, mbpol.f90:218-226, 311-314)
-    const long long d0 = tot[0] * h->rank / h->nranks, d1 = tot[0] * (h->rank + 1) / h->nranks;
-    const long long t0 = tot[1] * h->rank / h->nranks, t1 = tot[1] * (h->rank + 1) / h->nranks;
-    h->nd_shard = d1 - d0; h->nt_shard = t1 - t0;
-    OutPtrs O = h->views();
+    // ---- 2B ---------------------------------------------------------------------------------------------------------
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
-    if (h->nd_shard > 0) {
-        const unsigned gd = (unsigned)((h->nd_shard + MBPOL_BS2 - 1) / MBPOL_BS2);
-        const int2* dl = h->dimers.p + d0;
+    if (h->est_nd > 0) {
+        const unsigned gd = (unsigned)((h->est_nd + MBPOL_BS2 - 1) / MBPOL_BS2);
         if (h->engine2b == 3)
-            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
+            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
         else
-            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->nd_shard, dl, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
+            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
         ++h->launches;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
-    if (h->nt_shard > 0) {
-        const unsigned gt = (unsigned)((h->nt_shard + MBPOL_BS3 - 1) / MBPOL_BS3);
-        const int* tl = h->trimers.p + 3 * t0;
-        // incidence lists of the shard: count -> exclusive scan -> fill
-        CUDA_TRY(h, h->rec.reserve((size_t)h->nt_shard * MBPOL_REC3));
-        CUDA_TRY(h, h->inc.reserve((size_t)3 * h->nt_shard));
-        CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
+    // ---- 3B: incidence lists of the shard (count -> exclusive scan -> fill), records, gather -----------------------------
+    if (h->est_nt > 0) {
+        const unsigned gt = (unsigned)((h->est_nt + MBPOL_BS3 - 1) / MBPOL_BS3);
+        const unsigned gi = (unsigned)std::min<long long>((3 * h->est_nt + 255) / 256, 1 << 20);
         CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
         CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
-        const unsigned gi = (unsigned)((3 * h->nt_shard + 255) / 256);
-        k_inc_count<<<gi, 256, 0, s>>>(h->nt_shard, tl, h->inc_off.p);
+        k_inc_count<<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p);
         if (int rc = scan_int(h, h->inc_off.p, h->inc_off.p, nw + 1)) return rc;
-        k_inc_fill<<<gi, 256, 0, s>>>(h->nt_shard, tl, h->inc_off.p, h->inc_cur.p, h->inc.p);
+        k_inc_fill<<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p, h->inc_cur.p, h->inc.p);
+        CUDA_TRY(h, cudaEventRecord(h->ev[5], s));
         if (h->engine == 4)
-            k_trimers<4><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_sym3b[h->device], h->rec.p);
+            k_trimers<4><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_sym3b[h->device], h->rec.p);
         else if (h->engine == 3)
-            k_trimers<3><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_fat3b[h->device], h->rec.p);
+            k_trimers<3><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_fat3b[h->device], h->rec.p);
         else
-            k_trimers<1><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->nt_shard, tl, nw, h->mono.p, h->C, g_tape3b[h->device], h->rec.p);
-        k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, tl, h->rec.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
-        h->launches += 4;
-        ++h->launches;
+            k_trimers<1><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_tape3b[h->device], h->rec.p);
+        CUDA_TRY(h, cudaEventRecord(h->ev[6], s));
+        k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, h->trimers.p, h->rec.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        CUDA_TRY(h, cudaEventRecord(h->ev[7], s));
+        h->launches += 6;
+    } else {
+        for (int k = 5; k < 8; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
     if (h->have_vel) {
         k_flux<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
         ++h->launches;
     }
+    CUDA_TRY(h, cudaEventRecord(h->ev[8], s));
+    // ---- reduction over the ranks (NCCL over NVLink, on this stream): forces, per-atom arrays, scalars, weights -------------
+    if (h->reduce_mode && h->comm) {
+        if (h->reduce_mode == 2) {
+            NCCL_TRY(h, ncclReduceScatter(h->out.p, h->out.p + (size_t)h->rank * h->chunk(), h->chunk(), ncclDouble, ncclSum, h->comm, s));
+            NCCL_TRY(h, ncclAllReduce(O.scal, O.scal, (size_t)NSCAL * h->nbeads, ncclDouble, ncclSum, h->comm, s));
+        } else {
+            NCCL_TRY(h, ncclAllReduce(h->out.p, h->out.p, h->out_count(), ncclDouble, ncclSum, h->comm, s));
+        }
+        NCCL_TRY(h, ncclAllReduce(h->weight.p, h->weight.p, (size_t)nw, ncclInt, ncclSum, h->comm, s));
+        h->launches += 3;
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev[4], s));
+    // ---- the one read-back of the step: counts, overflow flag, weights ---------------------------------------------------
+    CUDA_TRY(h, cudaMemcpyAsync(h->back->counts, h->counts.p, 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(&h->back->flag, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->back->tail, O.scal + S_ND, 24, cudaMemcpyDeviceToHost, s));      // S_ND, S_NT, S_OVF
+    if (h->nranks > 1) {
+        if (!h->host_weight) CUDA_TRY(h, cudaMallocHost(&h->host_weight, (size_t)(nw + 1) * 4));
+        CUDA_TRY(h, cudaMemcpyAsync(h->host_weight, h->weight.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (h->back->flag == 1) { h->err = "neighbour capacity exceeded (NB2_CAP/NB3_CAP): unphysical density"; return MBPOL_B200_ECAPACITY; }
+    if (h->back->tail[2] > 0.0) {      // (all-reduced when a communicator is attached: every rank takes this branch together)
+        h->est_nd = h->back->counts[2]; h->est_nt = h->back->counts[3];
+        return -1;       // an estimate was too small somewhere: the caller repeats the step with exact sizes
+    }
+    h->nd_shard = h->back->counts[0]; h->nt_shard = h->back->counts[1];
+    h->est_nd = h->nd_shard; h->est_nt = h->nt_shard;
+    // box totals: the counts rode through the reduction in the scalar block (bead 0); without one, the shard is all this rank knows
+    h->nd_total = (long long)(h->back->tail[0] + 0.5); h->nt_total = (long long)(h->back->tail[1] + 0.5);
+    h->have_weight = h->nranks > 1 && h->reduce_mode && h->comm;      // without a communicator the weights of the other ranks are unknown
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);
     cudaEventElapsedTime(&h->ms[3], h->ev[0], h->ev[4]);
+    cudaEventElapsedTime(&h->ms[4], h->ev[5], h->ev[6]);      // k_trimers alone (the roofline kernel)
+    cudaEventElapsedTime(&h->ms[5], h->ev[6], h->ev[7]);      // k_trimers_gather
+    cudaEventElapsedTime(&h->ms[6], h->ev[8], h->ev[4]);      // reduction
+    cudaEventElapsedTime(&h->ms[7], h->ev[2], h->ev[5]);      // incidence lists
     return MBPOL_B200_OK;
+}
+
+int mbpol_b200_compute(mbpol_b200_handle* h)
+{
+    if (!h || !h->uploaded) return MBPOL_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = compute_once(h, h->est_nd >= 0 && h->est_nt >= 0);
+    if (rc == -1) {      // rare: the lists outgrew the previous step's counts by > 25 % (collective decision, see k_publish_counts)
+        rc = compute_once(h, false);
+        if (rc == -1) { h->err = "work lists changed size during the step"; return MBPOL_B200_ECUDA; }
+    }
+    return rc;
 }
 
 int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* fzz, double* eng2, double* vir2, double* eng3,
@@ -791,19 +982,26 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         h->pinned_cap = cnt;
     }
     double* P = h->pinned;
+    // After a reduce-scatter this rank holds (and returns) only its slice [lo, hi) of the flat per-atom part; the caller's sum over the
+    // ranks (gdsum, dlpoly_cmd.f:2551, 2568; heatcurrent.f90:1129-1259) completes the arrays exactly as it does for the reference.
+    const bool slice = h->reduce_mode == 2 && h->comm && h->nranks > 1;
+    const size_t lo = slice ? std::min((size_t)h->rank * h->chunk(), h->atom_count()) : 0;
+    const size_t hi = slice ? std::min((size_t)(h->rank + 1) * h->chunk(), h->atom_count()) : h->atom_count();
     // Copy only what the caller asked for, in pieces with an event behind each piece: the host threads accumulate piece k
     // into the caller's arrays (the reference's "+=" semantics) while piece k+1 is still crossing PCIe.
     struct Job { double* dst; size_t off, len; };
-    std::vector<Job> jobs = {{fxx, 0, n}, {fyy, n, n}, {fzz, 2 * n, n}};
-    if (atomic_energy) jobs.push_back({atomic_energy, 3 * n, n});
-    for (int half = 0; half < 2; ++half) {
-        const size_t a = 9 * n * half / 2, b = 9 * n * (half + 1) / 2;
-        if (atomic_stress) jobs.push_back({atomic_stress + a, 4 * n + a, b - a});
-    }
-    for (int half = 0; half < 2; ++half) {
-        const size_t a = 9 * n * half / 2, b = 9 * n * (half + 1) / 2;
-        if (atomic_fdecomp) jobs.push_back({atomic_fdecomp + a, 13 * n + a, b - a});
-    }
+    std::vector<Job> jobs;
+    auto add = [&](double* dst, size_t a, size_t b) {      // caller array dst covers flat [a, b)
+        if (!dst) return;
+        const size_t x = std::max(a, lo), y = std::min(b, hi);
+        if (x >= y) return;
+        const size_t piece = std::max<size_t>((y - x + 1) / 2, 1 << 16);
+        for (size_t q = x; q < y; q += piece) jobs.push_back({dst + (q - a), q, std::min(piece, y - q)});
+    };
+    add(fxx, 0, n); add(fyy, n, 2 * n); add(fzz, 2 * n, 3 * n);
+    add(atomic_energy, 3 * n, 4 * n);
+    add(atomic_stress, 4 * n, 13 * n);
+    add(atomic_fdecomp, 13 * n, 22 * n);
     while (h->dl_ev.size() < jobs.size() + 1) {
         cudaEvent_t e;
         CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -815,9 +1013,11 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         CUDA_TRY(h, cudaEventRecord(h->dl_ev[k], h->stream));
         total += jobs[k].len;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(P + 22 * n, h->out.p + 22 * n, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
+    const size_t so = h->scal_offset();
+    CUDA_TRY(h, cudaMemcpyAsync(P + so, h->out.p + so, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
-    const unsigned nth = total < (1u << 18) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nth = total < (1u << 18) ? 1u : std::min(8u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
     auto work = [&](unsigned t) {
         cudaSetDevice(h->device);
         for (size_t k = 0; k < jobs.size(); ++k) {
@@ -836,14 +1036,20 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         for (auto& t : th) t.join();
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const bool reduced = h->reduce_mode && h->comm && h->nranks > 1;
     for (int b = 0; b < h->nbeads; ++b) {     // scalars are per bead: eng2[b], ..., stress[9*b + q], jflux[9*b + q]
-        const double* sc = P + 22 * n + (size_t)b * NSCAL;
-        if (eng2) eng2[b] += sc[S_ENG2];
-        if (vir2) vir2[b] += sc[S_VIR2];
-        if (eng3) eng3[b] += sc[S_ENG3];
-        if (vir3) vir3[b] += sc[S_VIR3];
-        if (stress) for (int q = 0; q < 9; ++q) stress[9 * b + q] += sc[S_STRESS + q];
-        if (jflux) for (int q = 0; q < 9; ++q) jflux[9 * b + q] = sc[S_JFLUX + q];
+        const double* sc = P + so + (size_t)b * NSCAL;
+        // after an in-library reduction every rank holds the TOTALS: only rank 0 adds them, so that the caller's gdsum of the
+        // four scalars (mbpol.f90:395-431) and of stress (dlpoly_cmd.f:2568) still gives the right sums
+        const bool mine = !reduced || h->rank == 0;
+        if (mine) {
+            if (eng2) eng2[b] += sc[S_ENG2];
+            if (vir2) vir2[b] += sc[S_VIR2];
+            if (eng3) eng3[b] += sc[S_ENG3];
+            if (vir3) vir3[b] += sc[S_VIR3];
+            if (stress) for (int q = 0; q < 9; ++q) stress[9 * b + q] += sc[S_STRESS + q];
+        }
+        if (jflux) for (int q = 0; q < 9; ++q) jflux[9 * b + q] = mine ? sc[S_JFLUX + q] : 0.0;
     }
     return MBPOL_B200_OK;
 }
@@ -856,6 +1062,18 @@ int mbpol_b200_forces(mbpol_b200_handle* h, int imcon, const double* cell, int n
     if (!h) return MBPOL_B200_EINVAL;
     if (atomic_stress && !(h->flags & MBPOL_B200_WANT_ATOMIC_STRESS)) {
         h->err = "atomic_stress requested but the handle was created without MBPOL_B200_WANT_ATOMIC_STRESS";
+        return MBPOL_B200_EINVAL;
+    }
+    if (atomic_energy && !(h->flags & MBPOL_B200_WANT_ATOMIC_ENERGY)) {
+        h->err = "atomic_energy requested but the handle was created without MBPOL_B200_WANT_ATOMIC_ENERGY";
+        return MBPOL_B200_EINVAL;
+    }
+    if (atomic_fdecomp && !(h->flags & MBPOL_B200_WANT_FDECOMP)) {
+        h->err = "atomic_fdecomp requested but the handle was created without MBPOL_B200_WANT_FDECOMP";
+        return MBPOL_B200_EINVAL;
+    }
+    if (jflux && !(vxx && vyy && vzz)) {
+        h->err = "jflux requested without velocities (vxx, vyy, vzz)";
         return MBPOL_B200_EINVAL;
     }
     if (int rc = mbpol_b200_upload(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, vxx, vyy, vzz)) return rc;
@@ -895,10 +1113,10 @@ int mbpol_b200_get_lists(mbpol_b200_handle* h, int* dimers, long long dimer_cap,
 {
     if (!h) return MBPOL_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (dimers && dimer_cap >= h->nd_total && h->nd_total > 0)
-        CUDA_TRY(h, cudaMemcpy(dimers, h->dimers.p, (size_t)h->nd_total * 8, cudaMemcpyDeviceToHost));
-    if (trimers && trimer_cap >= h->nt_total && h->nt_total > 0)
-        CUDA_TRY(h, cudaMemcpy(trimers, h->trimers.p, (size_t)h->nt_total * 12, cudaMemcpyDeviceToHost));
+    if (dimers && dimer_cap >= h->nd_shard && h->nd_shard > 0)
+        CUDA_TRY(h, cudaMemcpy(dimers, h->dimers.p, (size_t)h->nd_shard * 8, cudaMemcpyDeviceToHost));
+    if (trimers && trimer_cap >= h->nt_shard && h->nt_shard > 0)
+        CUDA_TRY(h, cudaMemcpy(trimers, h->trimers.p, (size_t)h->nt_shard * 12, cudaMemcpyDeviceToHost));
     return MBPOL_B200_OK;
 }
 
@@ -907,6 +1125,22 @@ int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches
     if (!h) return MBPOL_B200_EINVAL;
     if (ms) std::copy(h->ms, h->ms + 4, ms);
     if (launches) *launches = h->launches;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_phase_times(mbpol_b200_handle* h, float* ms, int n)
+{
+    if (!h || !ms || n < 0) return MBPOL_B200_EINVAL;
+    for (int k = 0; k < n; ++k) ms[k] = k < 8 ? h->ms[k] : 0.f;
+    return MBPOL_B200_OK;
+}
+
+int mbpol_b200_shard(mbpol_b200_handle* h, int* first_water, int* n_waters, long long* scalar_offset)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (first_water) *first_water = h->w0;
+    if (n_waters) *n_waters = h->nown;
+    if (scalar_offset) *scalar_offset = (long long)h->scal_offset();
     return MBPOL_B200_OK;
 }
 

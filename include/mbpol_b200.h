@@ -24,6 +24,8 @@
 #ifndef MBPOL_B200_H
 #define MBPOL_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -61,11 +63,34 @@ int mbpol_b200_forces_batched(mbpol_b200_handle* handle, int nbeads, int imcon, 
                               double* atomic_energy, double* atomic_stress, double* atomic_fdecomp,
                               const double* vxx, const double* vyy, const double* vzz, double* jflux);
 
-/* Work split exactly like `do t = bead_rank, n-1, bead_size` (mbpol.f90:218-226, 311-314) in spirit: with
- * (rank, nranks) != (0,1) the handle evaluates only its contiguous shard of the dimer and trimer lists and
- * the caller's existing gdsum over comm_bead (dlpoly_cmd.f:2551, 2568; heatcurrent.f90:1129-1259), or an NCCL
- * all-reduce over mbpol_b200_device_outputs, completes the sum.  Default (0,1). */
+/* Work split in the spirit of `do t = bead_rank, n-1, bead_size` (mbpol.f90:218-226, 311-314): with (rank, nranks) != (0,1) the
+ * handle BUILDS AND EVALUATES only its shard of the lists -- the dimers whose first water and the trimers whose centre water lie
+ * in this rank's contiguous water range -- and the caller's existing gdsum over comm_bead (dlpoly_cmd.f:2551, 2568;
+ * heatcurrent.f90:1129-1259) completes the sums.  Default (0,1); uniform water ranges. */
 int mbpol_b200_set_shard(mbpol_b200_handle* handle, int rank, int nranks);
+
+/* NCCL inside the boundary (the in-library analogue of those gdsum calls, over NVLink instead of PCIe + MPI).  One process per GPU:
+ * rank 0 calls _comm_unique_id and ships the 128 bytes to the others by the host's own means (MPI_Bcast in a Fortran host);
+ * every rank then calls _comm_init, which also fixes the handle's shard to (rank, nranks).  From then on every step ends with a
+ * reduction on the handle's stream:
+ *   mode 2 (default)  ncclReduceScatter of the per-atom part: rank r holds, downloads and ADDS only slice r of the packed buffer
+ *                     (1/nranks of the PCIe traffic per rank); the caller's gdsum still completes the arrays, as for the reference.
+ *   mode 1            ncclAllReduce: every rank holds everything; the per-atom arrays are returned by every rank (divide or skip the
+ *                     caller's gdsum accordingly).
+ *   mode 0            no reduction (shards only).
+ * In modes 1 and 2 the scalars (eng2, vir2, eng3, vir3, stress, jflux) are all-reduced and returned by RANK 0 ONLY (zero from the
+ * others), so that the caller's gdsum of them stays correct.  The shard boundaries follow the per-water work of the previous step
+ * (weights = 4 x trimers + dimers, all-reduced with the results), so the ranks stay balanced as the liquid moves. */
+#define MBPOL_B200_UNIQUE_ID_BYTES 128
+int mbpol_b200_comm_unique_id(void* id /* MBPOL_B200_UNIQUE_ID_BYTES */);
+int mbpol_b200_comm_init(mbpol_b200_handle* handle, int rank, int nranks, const void* id);
+int mbpol_b200_comm_mode(mbpol_b200_handle* handle, int mode);
+/* Host arithmetic behind the shard boundaries (every rank computes the same cut): bounds[r] .. bounds[r+1] = waters of rank r. */
+void mbpol_b200_shard_bounds(int nw, int nranks, const int* weight /* nw entries or NULL = uniform */, int* bounds /* nranks + 1 */);
+/* cudaHostRegister / cudaHostUnregister for the caller's coordinate and force arrays (pin them ONCE: the per-step copies then run
+ * at full PCIe speed and asynchronously). */
+int mbpol_b200_host_register(void* p, size_t bytes);
+int mbpol_b200_host_unregister(void* p);
 
 /* The drop-in for mbpol_forces.  Argument meaning as in mbpol.f90:98-116; wat_monomer_ener is unused by the
  * reference's live code path and therefore absent.  eng2/vir2/eng3/vir3 are the four scalars the reference
@@ -92,8 +117,9 @@ int mbpol_b200_forces(mbpol_b200_handle* handle, int imcon, const double* cell, 
  *   _download: device -> host copy and accumulation into the caller's arrays (same semantics as _forces)
  * mbpol_b200_device_outputs exposes the packed FP64 device buffer
  *   [ fxx | fyy | fzz | atomic_energy | atomic_stress(9) | atomic_fdecomp(9) ](each mxatms) [ scalars(32) ]
- *   scalars (32 per bead): 0 eng2, 1 vir2, 2 eng3, 3 vir3, 4..12 stress, 13..21 jflux, rest reserved
- * so that one ncclAllReduce(sum, double) over `count` elements finishes a multi-GPU step. */
+ *   scalars (32 per bead, at the offset mbpol_b200_shard reports): 0 eng2, 1 vir2, 2 eng3, 3 vir3, 4..12 stress, 13..21 jflux,
+ *   22 / 23 dimers / trimers of the shard, rest reserved
+ * so that one all-reduce(sum, double) over `count` elements finishes a multi-GPU step when the caller reduces itself. */
 int mbpol_b200_upload(mbpol_b200_handle* handle, int imcon, const double* cell, int nttm2, const int* listttm2,
                       int mxatms, const double* xxx, const double* yyy, const double* zzz,
                       const double* vxx, const double* vyy, const double* vzz);
@@ -102,14 +128,21 @@ int mbpol_b200_download(mbpol_b200_handle* handle, double* fxx, double* fyy, dou
                         double* eng2, double* vir2, double* eng3, double* vir3, double* stress,
                         double* atomic_energy, double* atomic_stress, double* atomic_fdecomp, double* jflux);
 int mbpol_b200_device_outputs(mbpol_b200_handle* handle, void** dev_ptr, long long* count);
+/* this rank's water range and the offset of the scalar block inside the packed buffer (= 22*mxatms rounded up to nranks equal,
+ * even chunks: the unit of the reduce-scatter) */
+int mbpol_b200_shard(mbpol_b200_handle* handle, int* first_water, int* n_waters, long long* scalar_offset);
 void* mbpol_b200_stream(mbpol_b200_handle* handle);   /* the cudaStream_t every kernel of the handle runs on */
 
-/* Introspection for tests / benchmarks (valid after _compute or _forces). */
+/* Introspection for tests / benchmarks (valid after _compute or _forces).  The *_total counts are box totals once a reduction
+ * has run (in-library communicator) and equal the shard counts otherwise; _get_lists returns THIS RANK's shard of the lists. */
 int mbpol_b200_counts(mbpol_b200_handle* handle, long long* n_dimers_total, long long* n_trimers_total,
                       long long* n_dimers_shard, long long* n_trimers_shard);
 int mbpol_b200_get_lists(mbpol_b200_handle* handle, int* dimers /*2*n*/, long long dimer_cap,
                          int* trimers /*3*n*/, long long trimer_cap);   /* 0-based water indices, i<j(<k), full lists */
 int mbpol_b200_kernel_times(mbpol_b200_handle* handle, float* ms /*[4]: lists, 2B, 3B, total*/, long long* launches);
+/* finer split, n <= 8: 0 lists, 1 2B, 2 3B (incidence lists + k_trimers + gather), 3 whole step incl. reduction, 4 k_trimers alone
+ * (the roofline kernel), 5 k_trimers_gather, 6 reduction over the ranks, 7 incidence lists */
+int mbpol_b200_phase_times(mbpol_b200_handle* handle, float* ms, int n);
 
 /* FP64 roofline probe: best-of-3 throughput of independent register-resident DFMA chains on the current device
  * (2 flop per DFMA), the measured denominator for the "fraction of FP64 FMA peak" figures. */

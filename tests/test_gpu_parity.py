@@ -150,18 +150,23 @@ def test_shards_sum_to_the_whole(mb, synth):
     box = synth.make_water_box(256)
     h = mb.mbpol_init(box["nttm2"], flags=7)
     full = mb.run_box(h, box, want_stress=True)
+    d_all, t_all = mb.mbpol_lists(h)
     acc = None
-    ntri = 0
+    dl, tl = [], []
     for r in range(3):
         mb.mbpol_set_shard(h, r, 3)
         p = mb.run_box(h, box, want_stress=True)
-        ntri += mb.mbpol_counts(h)["trimers_shard"]
+        d, t = mb.mbpol_lists(h)                       # this rank's shard: the lists it built itself
+        sh = mb.mbpol_shard(h)
+        assert np.all((d[:, 0] >= sh["first_water"]) & (d[:, 0] < sh["first_water"] + sh["n_waters"]))
+        dl.append(d); tl.append(t)
         if acc is None:
             acc = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.items()}
         else:
             for k, v in p.items():
                 acc[k] = acc[k] + v
-    assert ntri == mb.mbpol_counts(h)["trimers"]
+    # the shards partition the lists of the whole box exactly
+    assert np.array_equal(sort_rows(np.concatenate(dl)), sort_rows(d_all)) and np.array_equal(sort_rows(np.concatenate(tl)), sort_rows(t_all))
     mb.mbpol_fini(h)
     compare(acc, full, ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp", "stress", "jflux"))
 
