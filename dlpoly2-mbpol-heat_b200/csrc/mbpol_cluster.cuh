@@ -7,6 +7,7 @@
 #include "mbpol_b200.h"
 #include "mbpol_device.cuh"
 
+extern __constant__ int c_gather_vp2[31];     // 2B: variable n with the two molecules swapped -> original variable
 extern __constant__ int c_gather_vp[3][36];  // slot s: variable n of the relabelled frame (molecules 0 <-> s swapped) -> original variable
 
 namespace mbpol_k {
@@ -151,7 +152,7 @@ k_trimers(const long long* __restrict__ pcount, const int* __restrict__ tri, int
         trimer_record(xv, gp, Epoly, sw, out);
     }
     __syncthreads();      // every thread has read its last gradient column: the column area is free
-    double* stage = reinterpret_cast<TapeSmem<36>*>(dyn_smem)->xs[0];
+    double* stage = ENGINE == 4 ? reinterpret_cast<SymSmem*>(dyn_smem)->xs[0] : reinterpret_cast<TapeSmem<36>*>(dyn_smem)->xs[0];
     static_assert(sizeof(double) * MBPOL_REC3_STRIDE * TAPE_BS <= 2 * sizeof(double) * 37 * TAPE_BS, "staging area");
 #pragma unroll
     for (int n = 0; n < MBPOL_REC3; ++n) stage[threadIdx.x * MBPOL_REC3_STRIDE + n] = out[n];
@@ -186,7 +187,10 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef MBPOL_GATHER_MINBLOCKS
+#define MBPOL_GATHER_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, MBPOL_GATHER_MINBLOCKS)
 k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restrict__ inc, const int* __restrict__ tri,
                  const double* __restrict__ rec, const double* __restrict__ mono, const int* __restrict__ list,
                  const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
@@ -320,123 +324,223 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
 }
 
 // incidence lists: water -> (trimer << 2 | slot) for the trimers [0, ntri) of this shard
+template <int M>      // M = 3: trimers (int[3]), M = 2: dimers (int2)
 __global__ void k_inc_count(const long long* __restrict__ pcount, const int* __restrict__ tri, int* __restrict__ cnt)
 {
-    const long long n3 = 3 * *pcount;
+    const long long n3 = M * *pcount;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) atomicAdd(&cnt[tri[i]], 1);
 }
+template <int M>
 __global__ void k_inc_fill(const long long* __restrict__ pcount, const int* __restrict__ tri, const int* __restrict__ off, int* __restrict__ cur,
                            unsigned* __restrict__ inc)
 {
-    const long long n3 = 3 * *pcount;
+    const long long n3 = M * *pcount;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
         const int w = tri[i];
-        inc[off[w] + atomicAdd(&cur[w], 1)] = (unsigned)((i / 3) << 2) | (unsigned)(i % 3);
+        inc[off[w] + atomicAdd(&cur[w], 1)] = M == 3 ? ((unsigned)((i / 3) << 2) | (unsigned)(i % 3)) : ((unsigned)((i / 2) << 1) | (unsigned)(i % 2));
     }
 }
 
 #endif   // MBPOL_GATHER_KERNELS
 
 // ---------------------------------------------------------------------------------------------------------
-// K2: dimers
+// K2 phase 1: one thread per accepted dimer of this shard -- geometry (do_dimer's imaging, mbpol.f90:496-509; origin moved to
+// O_j), lone pairs, 31 variables, polynomial, switch -> a 34-double record (dimer_record).  Staged and stored like the 3B records.
 // ---------------------------------------------------------------------------------------------------------
+#define MBPOL_REC2_STRIDE 36
+
+__device__ __forceinline__ void dimer_geometry(int nw, const double* __restrict__ mono, const CellInfo& C, int mi, int mj, double (&w)[18])
+{
+    double wi[9], wj[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        wi[c] = mono[(size_t)c * nw + mi];
+        wj[c] = mono[(size_t)c * nw + mj];
+    }
+    double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+    image_vec(C, a0, a1, a2);
+    const double ra[3] = {a0, a1, a2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        w[c] = ra[c];
+        w[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+        w[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+        w[9 + c] = 0.0;
+        w[12 + c] = wj[3 + c] - wj[c];
+        w[15 + c] = wj[6 + c] - wj[c];
+    }
+}
+
 template <int ENGINE>
 __global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
-k_dimers(const long long* __restrict__ pcount, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, const int* __restrict__ list,
-         const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags,
-         const double* __restrict__ tape)
+k_dimers(const long long* __restrict__ pcount, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, CellInfo C,
+         const double* __restrict__ tape, double* __restrict__ rec)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     const long long ndim = *pcount;
-    for (long long first = (long long)blockIdx.x * blockDim.x; first < ndim; first += (long long)gridDim.x * blockDim.x) {
-    const long long t0_ = first + threadIdx.x;
-    bool valid = t0_ < ndim;
-    const long long t = valid ? t0_ : ndim - 1;
     const PolyCtx ctx{dyn_smem, tape};
-    double sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int bead = -1;
-    {
-        const int mi = dim[t].x, mj = dim[t].y;
-        if (valid) bead = mi / O.nwb;
-        double wi[9], wj[9], w[18];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            wi[c] = mono[(size_t)c * nw + mi];
-            wj[c] = mono[(size_t)c * nw + mj];
+    for (long long first = (long long)blockIdx.x * blockDim.x; first < ndim; first += (long long)gridDim.x * blockDim.x) {
+        const long long t0_ = first + threadIdx.x;
+        const long long t = t0_ < ndim ? t0_ : ndim - 1;     // idle lanes shadow the last dimer: the tape walk has CTA barriers
+        double out[MBPOL_REC2];
+        {
+            double w[18];
+            dimer_geometry(nw, mono, C, dim[t].x, dim[t].y, w);
+            dimer_record<ENGINE>(w, out, ctx);
         }
-        double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
-        image_vec(C, a0, a1, a2);                       // do_dimer, mbpol.f90:496-509; origin moved to O_j
-        const double ra[3] = {a0, a1, a2};
+        __syncthreads();      // every thread has read its last gradient column: the column area is free
+        double* stage = reinterpret_cast<TapeSmem<31>*>(dyn_smem)->xs[0];
+        static_assert(MBPOL_REC2_STRIDE <= 2 * 32, "staging area");
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            w[c] = ra[c];
-            w[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
-            w[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
-            w[9 + c] = 0.0;
-            w[12 + c] = wj[3 + c] - wj[c];
-            w[15 + c] = wj[6 + c] - wj[c];
+        for (int n = 0; n < MBPOL_REC2; ++n) stage[threadIdx.x * MBPOL_REC2_STRIDE + n] = out[n];
+        __syncthreads();
+        const long long left = ndim - first;
+        const int nvalid = left < (long long)blockDim.x ? (int)left : (int)blockDim.x;
+        double2* dst = reinterpret_cast<double2*>(rec + (size_t)first * MBPOL_REC2);
+        for (int i = threadIdx.x; i < nvalid * (MBPOL_REC2 / 2); i += blockDim.x) {
+            const int tr = i / (MBPOL_REC2 / 2), pr = i % (MBPOL_REC2 / 2);
+            dst[i] = *reinterpret_cast<const double2*>(stage + tr * MBPOL_REC2_STRIDE + 2 * pr);
         }
-        double E, g[18];
-        double fm[108];
-        const bool want_s = (flags & MBPOL_B200_WANT_ATOMIC_STRESS) != 0;
-        dimer_eval<ENGINE>(w, E, g, want_s ? fm : nullptr, ctx);
-        const double eu = MBPOL_ENGUNIT;
-        const int o[2] = {list[3 * mi], list[3 * mj]};
-        if (valid) {
-        sc[0] = E * eu;
+        __syncthreads();      // the staged records are out before the next tile overwrites the columns
+    }
+}
+
+#ifdef MBPOL_GATHER_KERNELS
+// ---------------------------------------------------------------------------------------------------------
+// K2 phase 2: GATHER, one warp per water w over its dimer incidences (dimer << 1 | slot).  The dimer is rebuilt as phase 1 saw it,
+// the two molecules are swapped when w is the second one, and the rows of the folded pair matrix that belong to w's atoms
+// (dimer_rows_a) give everything do_dimer accumulates for them (mbpol.f90:519-654, 732-786): force = -row sum, E/6 per atom, W,
+// the (non-symmetric) per-atom stress S_i(a,b) = 1/2 eu sum_j (r_i - r_j)_a FM[i][j]_b, virial / stress / energy scalars.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2)
+k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restrict__ inc, const int2* __restrict__ dim,
+                const double* __restrict__ rec, const double* __restrict__ mono, const int* __restrict__ list,
+                const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool active = w < nw;
+    const int beg = active ? inc_off[w] : 0, end = active ? inc_off[w + 1] : 0;
+    const bool want_e = flags & MBPOL_B200_WANT_ATOMIC_ENERGY, want_w = flags & MBPOL_B200_WANT_FDECOMP, want_s = flags & MBPOL_B200_WANT_ATOMIC_STRESS;
+    const double eu = MBPOL_ENGUNIT;
+    double G[9], A[27], S[27], sc[8], esum = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const int atom = o[a / 3] - 1 + (a % 3);
+    for (int i = 0; i < 9; ++i) G[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) { A[i] = 0.0; S[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = 0.0;
+    for (int i = beg + lane; i < end; i += 32) {
+        const unsigned code = inc[i];
+        const int t = (int)(code >> 1), s = (int)(code & 1u);
+        const int2 m2 = dim[t];
+        double w0[18], wv[18];
+        dimer_geometry(nw, mono, C, m2.x, m2.y, w0);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {       // relabel: the gathering water becomes molecule a
+            wv[c] = s ? w0[9 + c] : w0[c];
+            wv[9 + c] = s ? w0[c] : w0[9 + c];
+        }
+        double xc[30];
+        dimer_sites(wv, xc);
+        const double* R = rec + (size_t)t * MBPOL_REC2;
+        double c[31];
+#pragma unroll
+        for (int n = 0; n < 31; ++n) c[n] = R[s ? c_gather_vp2[n] : n];
+        double fm[3][6][3];
+        dimer_rows_a(xc, c, R[32], fm);
+        const double E = R[31];
+        if (s == 0) sc[0] += E * eu;
+        esum += E;
+        double g[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    if (j != a) v += fm[a][j][k];
+                g[3 * a + k] = v;
+                G[3 * a + k] += v;
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
             const double gx = g[3 * a] * eu, gy = g[3 * a + 1] * eu, gz = g[3 * a + 2] * eu;
-            atomicAdd(O.fx + atom, -gx);
-            atomicAdd(O.fy + atom, -gy);
-            atomicAdd(O.fz + atom, -gz);
-            sc[1] += w[3 * a] * gx + w[3 * a + 1] * gy + w[3 * a + 2] * gz;
-            sc[2] -= w[3 * a] * gx; sc[3] -= w[3 * a] * gy; sc[4] -= w[3 * a] * gz;
-            sc[5] -= w[3 * a + 1] * gy; sc[6] -= w[3 * a + 1] * gz; sc[7] -= w[3 * a + 2] * gz;
+            sc[1] += wv[3 * a] * gx + wv[3 * a + 1] * gy + wv[3 * a + 2] * gz;
+            sc[2] -= wv[3 * a] * gx; sc[3] -= wv[3 * a] * gy; sc[4] -= wv[3 * a] * gz;
+            sc[5] -= wv[3 * a + 1] * gy; sc[6] -= wv[3 * a + 1] * gz; sc[7] -= wv[3 * a + 2] * gz;
         }
-        if (flags & MBPOL_B200_WANT_ATOMIC_ENERGY) {
-            const double e6 = (1.0 / 6.0) * E * eu;
+        if (want_s) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) atomicAdd(O.aeng + o[a / 3] - 1 + (a % 3), e6);
-        }
-        if (flags & MBPOL_B200_WANT_FDECOMP) {
-            double xs[3] = {0, 0, 0}, xraw[18];
+            for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const int atom = o[a / 3] - 1 + (a % 3);
-                xraw[3 * a] = xr[atom]; xraw[3 * a + 1] = yr[atom]; xraw[3 * a + 2] = zr[atom];
-                xs[0] += xraw[3 * a]; xs[1] += xraw[3 * a + 1]; xs[2] += xraw[3 * a + 2];
-            }
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const double f[3] = {-(1.0 / 6.0) * g[3 * a] * eu, -(1.0 / 6.0) * g[3 * a + 1] * eu, -(1.0 / 6.0) * g[3 * a + 2] * eu};
-                scatter_fdecomp(O, o[a / 3] - 1 + (a % 3), xraw + 3 * a, xs, 6, f);
-            }
-        }
-        if (want_s) {   // mbpol.f90:558-579: S_i(a,b) = 1/2*eu*sum_{j != i} (r_i - r_j)_a * FM[i][j]_b  (FM is NOT antisymmetric)
-            const size_t n = O.mxb;
-            for (int i = 0; i < 6; ++i) {
-                double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 for (int j = 0; j < 6; ++j) {
-                    if (i == j) continue;
-                    for (int a = 0; a < 3; ++a) {
-                        const double ra_ = w[3 * i + a] - w[3 * j + a];
-                        for (int b = 0; b < 3; ++b) S[a + 3 * b] += ra_ * fm[18 * i + 3 * j + b];
+                    if (j == a) continue;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const double ra = wv[3 * a + p] - wv[3 * j + p];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) S[9 * a + p + 3 * q] += ra * fm[a][j][q];
                     }
                 }
-                double* p = O.astress + tensor_base(O, o[i / 3] - 1 + (i % 3));
-                for (int q = 0; q < 9; ++q) atomicAdd(p + n * q, 0.5 * eu * S[q]);
+        }
+        if (want_w) {
+            double X[3] = {0, 0, 0};
+            const int oo[2] = {list[3 * m2.x] - 1, list[3 * m2.y] - 1};
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { X[0] += xr[oo[m] + k]; X[1] += yr[oo[m] + k]; X[2] += zr[oo[m] + k]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) A[9 * a + p + 3 * q] += X[p] * g[3 * a + q];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = warp_sum(G[i]);
+    esum = warp_sum(esum);
+    if (want_w) {
+#pragma unroll
+        for (int i = 0; i < 27; ++i) A[i] = warp_sum(A[i]);
+    }
+    if (want_s) {
+#pragma unroll
+        for (int i = 0; i < 27; ++i) S[i] = warp_sum(S[i]);
+    }
+    if (active && lane == 0 && end > beg) {
+        const int o = list[3 * w] - 1;
+        const size_t n = O.mxb;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int atom = o + a;
+            O.fx[atom] -= G[3 * a] * eu; O.fy[atom] -= G[3 * a + 1] * eu; O.fz[atom] -= G[3 * a + 2] * eu;
+            if (want_e) O.aeng[atom] += (1.0 / 6.0) * esum * eu;
+            if (want_w) {   // W_i = sum_c (6 x_i - X_c) (x) (-g_i eu / 6)
+                const double x3[3] = {xr[atom], yr[atom], zr[atom]};
+                double* p = O.afd + tensor_base(O, atom);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) p[n * (i + 3 * j)] += (1.0 / 6.0) * eu * A[9 * a + i + 3 * j] - x3[i] * G[3 * a + j] * eu;
+            }
+            if (want_s) {
+                double* p = O.astress + tensor_base(O, atom);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) p[n * q] += 0.5 * eu * S[9 * a + q];
             }
         }
-        }   // valid
     }
+    const int bead = active ? w / O.nwb : -1;
     double v2[2] = {sc[0], sc[1]};
     block_reduce_add_bead<2>(v2, O.scal, S_ENG2, bead);
     double st[9] = {sc[2], sc[3], sc[4], sc[3], sc[5], sc[6], sc[4], sc[6], sc[7]};
     block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
-    }
 }
+#endif   // MBPOL_GATHER_KERNELS
 
 // ---------------------------------------------------------------------------------------------------------
 // batched per-cluster kernels (legacy ABI / KAT tests)

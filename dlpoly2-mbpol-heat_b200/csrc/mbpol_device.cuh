@@ -282,6 +282,115 @@ __device__ __forceinline__ void lonepair_spread(const double* ohh, const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Box path, phase 1 (k_dimers): everything of x2b_v6x_p::operator() up to the per-variable force coefficients.
+// rec[n] = sw * dEpoly/dx_n * (dx_n/dr)/r  for the 31 variables: the pair vector of variable n = (p, q) is rec[n] (x_p - x_q);
+// rec[31] = sw * Epoly (the 2B energy, kcal/mol), rec[32] = Epoly * dsw/dr / rOO (switch gradient along Oa - Ob), rec[33] = 0.
+// Phase 2 (k_dimers_gather) folds these onto the atoms (dimer_rows_a).  A pair beyond r2f gives a zero record, like the
+// reference's early return (mbpol-2b-poly.cpp:370-371).
+// ---------------------------------------------------------------------------------------------------------
+#define MBPOL_REC2 34
+__device__ __forceinline__ void dimer_sites(const double* w, double (&xc)[30])
+{
+#pragma unroll
+    for (int i = 0; i < 18; ++i) xc[i] = w[i];
+    lonepair_sites(xc + 0, xc + 18, xc + 21);
+    lonepair_sites(xc + 9, xc + 24, xc + 27);
+}
+
+template <int ENGINE>
+__device__ __forceinline__ void dimer_record(const double* w, double (&rec)[MBPOL_REC2], const PolyCtx& ctx)
+{
+    double xc[30];
+    dimer_sites(w, xc);
+    const double dOO[3] = {w[0] - w[9], w[1] - w[10], w[2] - w[11]};
+    const double rOO = sqrt(dOO[0] * dOO[0] + dOO[1] * dOO[1] + dOO[2] * dOO[2]);
+    double xv[31], gp[31], gfac[31];
+#pragma unroll
+    for (int n = 0; n < 31; ++n) {
+        const int a = 3 * V2A[n], b = 3 * V2B[n];
+        const double dx = xc[a] - xc[b], dy = xc[a + 1] - xc[b + 1], dz = xc[a + 2] - xc[b + 2];
+        const double rr = sqrt(dx * dx + dy * dy + dz * dz);
+        const double k = mbpol_par.k2[V2K[n]];
+        const double r0 = (V2K[n] <= 1) ? 1.0 : 4.0;
+        const double e1 = exp(k * (r0 - rr));
+        const double ri = 1.0 / rr;
+        if (V2K[n] >= 2 && V2K[n] <= 4) {   // "coulomb" type: exp(k(r0-r))/r
+            const double val = e1 * ri;
+            xv[n] = val;
+            gfac[n] = -(k + ri) * val * ri;
+        } else {
+            xv[n] = e1;
+            gfac[n] = -k * e1 * ri;
+        }
+    }
+    double gsw;
+    const double sw = switch_fn(rOO, mbpol_par.r2i, mbpol_par.r2f, gsw);
+    const double gsr = gsw / rOO;
+    double Epoly;
+    static_assert(ENGINE == 1 || ENGINE == 3, "unknown polynomial engine");
+    if constexpr (ENGINE == 3) fat_eval<2, 31>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
+    else tape_eval<2, 31>(ctx.tape, xv, gp, Epoly, *reinterpret_cast<TapeSmem<31>*>(ctx.smem));
+    const bool inside = !(rOO > mbpol_par.r2f);
+#pragma unroll
+    for (int n = 0; n < 31; ++n) rec[n] = inside ? sw * gp[n] * gfac[n] : 0.0;
+    rec[31] = inside ? sw * Epoly : 0.0;
+    rec[32] = inside ? gsr * Epoly : 0.0;
+    rec[33] = 0.0;
+}
+
+// Phase 2: rows i = Oa, Ha1, Ha2 of the reference's folded pair force matrix FM[i][j], j = Oa Ha1 Ha2 Ob Hb1 Hb2
+// (mbpol-2b-poly.cpp:503-653, 665-679), from the per-variable coefficients c[31] (already x switch) of a dimer whose molecule a
+// is the gathering water.  Lone-pair contributions: the X sites of a are spread over a's atoms with the monomer::grads
+// formulas (linear, so all pair vectors towards one column are summed first); the X sites of b are lumped onto Ob.  The matrix
+// is NOT antisymmetric; the row sums are the gradient on the atoms of a.
+__device__ __forceinline__ void dimer_rows_a(const double (&xc)[30], const double (&c)[31], double gswE, double (&fm)[3][6][3])
+{
+    double gx[2][3][3];      // pair vectors on Xa1 / Xa2 towards the columns Ob, Hb1, Hb2
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) fm[i][j][k] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gx[s][j][k] = 0.0;
+#pragma unroll
+    for (int n = 0; n < 31; ++n) {
+        const int p = V2A[n], q = V2B[n];
+        if (p >= 3 && p < 6 && q >= 3 && q < 6) continue;                 // intramolecular b: no row of a
+        double d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) d[k] = c[n] * (xc[3 * p + k] - xc[3 * q + k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (p < 6 && q < 6) {                                          // atom - atom
+                if (p < 3) fm[p][q][k] += d[k];
+                if (q < 3) fm[q][p][k] -= d[k];
+            } else if (p >= 6 && p < 8 && q >= 3 && q < 6) gx[p - 6][q - 3][k] += d[k];      // Xa - (Hb): tmp[Xa][q] = d
+            else if (p == 3 && q >= 6 && q < 8) gx[q - 6][0][k] -= d[k];                     // Ob - Xa: tmp[Xa][Ob] = -d
+            else if (p >= 8 && q < 3) fm[q][3][k] -= d[k];                                   // Xb - Ha: tmp[Ha][Xb] = -d, lumped onto Ob
+            else if (p < 3 && q >= 8) fm[p][3][k] += d[k];                                   // Oa - Xb: tmp[Oa][Xb] = d, lumped onto Ob
+            else if (p >= 6 && p < 8 && q >= 8) gx[p - 6][0][k] += d[k];                     // Xa - Xb: spread over a, column Ob
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        lonepair_spread(&xc[0], gx[0][j], gx[1][j], acc, 3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) fm[i][3 + j][k] += acc[3 * i + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fm[0][3][k] += gswE * (xc[k] - xc[9 + k]);
+}
+
 // w[18]: imaged O,H,H of water a then water b (any common origin).  Outputs in kcal/mol: E, g[18];
 // fm (optional, 108 doubles, index 18*i+3*j+c) = the reference's folded pair force matrix with zero diagonal blocks.
 // Returns false (E = 0, g = 0) when rOO > r2f, like the reference's early return (mbpol-2b-poly.cpp:370-371).

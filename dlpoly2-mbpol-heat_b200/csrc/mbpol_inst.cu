@@ -15,7 +15,7 @@
 
 namespace mbpol_k {
 #if MBPOL_INST_WHICH == 2
-template __global__ void k_dimers<MBPOL_INST_ENGINE>(const long long*, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+template __global__ void k_dimers<MBPOL_INST_ENGINE>(const long long*, const int2*, int, const double*, CellInfo, const double*, double*);
 template __global__ void k_eval_dimers<MBPOL_INST_ENGINE>(int, const double*, double*, double*, double*, const double*);
 #else
 template __global__ void k_trimers<MBPOL_INST_ENGINE>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);

@@ -45,13 +45,14 @@ __constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
 __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
 __constant__ int c_gather_vp[3][36];
+__constant__ int c_gather_vp2[31];
 
 using namespace mbpol_k;
 
 // the (kernel, engine) instantiations live in mbpol_inst.cu
 namespace mbpol_k {
-extern template __global__ void k_dimers<1>(const long long*, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
-extern template __global__ void k_dimers<3>(const long long*, const int2*, int, const double*, const int*, const double*, const double*, const double*, CellInfo, OutPtrs, int, const double*);
+extern template __global__ void k_dimers<1>(const long long*, const int2*, int, const double*, CellInfo, const double*, double*);
+extern template __global__ void k_dimers<3>(const long long*, const int2*, int, const double*, CellInfo, const double*, double*);
 extern template __global__ void k_trimers<1>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
 extern template __global__ void k_trimers<3>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
 extern template __global__ void k_trimers<4>(const long long*, const int*, int, const double*, CellInfo, const double*, double*);
@@ -387,7 +388,8 @@ int default_engine_2b()
     if (e && std::string(e) == "fat") return 3;
     return MBPOL_DEFAULT_ENGINE_2B;
 }
-constexpr size_t SMEM2B = tape_smem_bytes(31, MBPOL_BS2, TAPE_CHUNK_DOUBLES), SMEM3B = tape_smem_bytes(36, MBPOL_BS3, TAPE_CHUNK_DOUBLES);
+constexpr size_t SMEM2B = tape_smem_bytes(31, MBPOL_BS2, TAPE_CHUNK_DOUBLES), SMEM3B = tape_smem_bytes(36, MBPOL_BS3, TAPE_CHUNK_DOUBLES),
+                 SMEM3S = tape_smem_bytes(36, MBPOL_BS3, SYM_CHUNK_DOUBLES);
 
 template <class K>
 cudaError_t allow_smem(K kernel, size_t bytes)
@@ -483,6 +485,19 @@ int upload_constants(int device)
                 if (vp[s][n] < 0) return 1;
             }
         if (cudaMemcpyToSymbol(c_gather_vp, vp, sizeof(vp)) != cudaSuccess) return 1;
+        // 2B: sites 0..9 = Oa Ha1 Ha2 Ob Hb1 Hb2 Xa1 Xa2 Xb1 Xb2; swapping the molecules maps site s -> sw[s]
+        static const int a2[31] = {1, 4, 0, 0, 3, 3, 1, 1, 2, 2, 0, 0, 3, 3, 0, 6, 6, 7, 7, 8, 8, 9, 9, 0, 0, 3, 3, 6, 6, 7, 7};
+        static const int b2[31] = {2, 5, 1, 2, 4, 5, 4, 5, 4, 5, 4, 5, 1, 2, 3, 4, 5, 4, 5, 1, 2, 1, 2, 8, 9, 6, 7, 8, 9, 8, 9};
+        static const int sw[10] = {3, 4, 5, 0, 1, 2, 8, 9, 6, 7};
+        int vp2[31];
+        for (int n = 0; n < 31; ++n) {
+            const int a = sw[a2[n]], b = sw[b2[n]];
+            vp2[n] = -1;
+            for (int k = 0; k < 31; ++k)
+                if ((a2[k] == a && b2[k] == b) || (a2[k] == b && b2[k] == a)) vp2[n] = k;
+            if (vp2[n] < 0) return 1;
+        }
+        if (cudaMemcpyToSymbol(c_gather_vp2, vp2, sizeof(vp2)) != cudaSuccess) return 1;
     }
     return 0;
 }
@@ -525,9 +540,9 @@ struct mbpol_b200_handle {
     CellInfo C;
     Grid G;
     int ncells = 0;
-    DevBuf<double> xyz, vel, mono, out, rec;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
+    DevBuf<double> xyz, vel, mono, out, rec, rec2;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
     DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur, weight;
-    DevBuf<unsigned> inc;                            // incidence lists water -> (trimer << 2 | slot) of the shard
+    DevBuf<unsigned> inc, inc2;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll, counts;
     DevBuf<char> scan_tmp;
@@ -639,7 +654,7 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     auto* h = new mbpol_b200_handle;
     h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine(); h->engine2b = default_engine_2b();
     if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_dimers<3>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
-        allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<4>, SMEM3B) != cudaSuccess) {
+        allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<4>, SMEM3S) != cudaSuccess) {
         delete h;
         return MBPOL_B200_ECUDA;
     }
@@ -865,6 +880,8 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, h->trimers.reserve((size_t)std::max<long long>(3 * cap3, 3)));
     CUDA_TRY(h, h->rec.reserve((size_t)std::max<long long>(cap3, 1) * MBPOL_REC3));
     CUDA_TRY(h, h->inc.reserve((size_t)std::max<long long>(3 * cap3, 3)));
+    CUDA_TRY(h, h->rec2.reserve((size_t)std::max<long long>(cap2, 1) * MBPOL_REC2));
+    CUDA_TRY(h, h->inc2.reserve((size_t)std::max<long long>(2 * cap2, 2)));
     if (nown > 0) {
         k_fill_dimers<<<go, TB, 0, s>>>(w0, nown, h->nb2.p, h->n2.p, h->off2.p, h->dimers.p, cap2, h->flag.p);
         k_trimers_enum<true><<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->nb3.p, h->n3.p, h->n2.p, nullptr, nullptr, h->off3.p, h->trimers.p, cap3, h->flag.p);
@@ -878,11 +895,18 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     if (h->est_nd > 0) {
         const unsigned gd = (unsigned)((h->est_nd + MBPOL_BS2 - 1) / MBPOL_BS2);
+        const unsigned gi = (unsigned)std::min<long long>((2 * h->est_nd + 255) / 256, 1 << 20);
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
+        k_inc_count<2><<<gi, 256, 0, s>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off.p);
+        if (int rc = scan_int(h, h->inc_off.p, h->inc_off.p, nw + 1)) return rc;
+        k_inc_fill<2><<<gi, 256, 0, s>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off.p, h->inc_cur.p, h->inc2.p);
         if (h->engine2b == 3)
-            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_fat2b[h->device]);
+            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_fat2b[h->device], h->rec2.p);
         else
-            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags, g_tape2b[h->device]);
-        ++h->launches;
+            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_tape2b[h->device], h->rec2.p);
+        k_dimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc2.p, h->dimers.p, h->rec2.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        h->launches += 6;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     // ---- 3B: incidence lists of the shard (count -> exclusive scan -> fill), records, gather -----------------------------
@@ -891,12 +915,12 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         const unsigned gi = (unsigned)std::min<long long>((3 * h->est_nt + 255) / 256, 1 << 20);
         CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
         CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
-        k_inc_count<<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p);
+        k_inc_count<3><<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p);
         if (int rc = scan_int(h, h->inc_off.p, h->inc_off.p, nw + 1)) return rc;
-        k_inc_fill<<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p, h->inc_cur.p, h->inc.p);
+        k_inc_fill<3><<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p, h->inc_cur.p, h->inc.p);
         CUDA_TRY(h, cudaEventRecord(h->ev[5], s));
         if (h->engine == 4)
-            k_trimers<4><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_sym3b[h->device], h->rec.p);
+            k_trimers<4><<<gt, MBPOL_BS3, SMEM3S, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_sym3b[h->device], h->rec.p);
         else if (h->engine == 3)
             k_trimers<3><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_fat3b[h->device], h->rec.p);
         else
@@ -1184,12 +1208,12 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
         const int eng = default_engine(), eng2 = default_engine_2b();
         ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B));
-        ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_trimers<4>, SMEM3B));
+        ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_trimers<4>, SMEM3S));
         if (nat3 == 18) {
             if (eng2 == 3) k_eval_dimers<3><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
             else k_eval_dimers<1><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);
         } else {
-            if (eng == 4) k_eval_trimers<4><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_sym3b[device]);
+            if (eng == 4) k_eval_trimers<4><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3S>>>(n, dw, dE, dg, dfm, g_sym3b[device]);
             else if (eng == 3) k_eval_trimers<3><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_fat3b[device]);
             else k_eval_trimers<1><<<(n + MBPOL_BS3 - 1) / MBPOL_BS3, MBPOL_BS3, SMEM3B>>>(n, dw, dE, dg, dfm, g_tape3b[device]);
         }

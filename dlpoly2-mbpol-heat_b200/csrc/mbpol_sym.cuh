@@ -13,12 +13,17 @@
 #endif
 #include MBPOL_SYM_HEADER
 
-static_assert(SYM_CHUNK_DOUBLES == TAPE_CHUNK_DOUBLES, "engines 1, 3 and 4 share the staging buffers");
+// own staging buffers: the chunk size of this engine is independent of engines 1 and 3 (smaller chunks leave room for more
+// per-thread columns, i.e. more warps per SM)
 extern __constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
 extern __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 extern __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
 
-typedef TapeSmem<36> SymSmem;
+struct SymSmem {
+    double buf[2][SYM_CHUNK_DOUBLES];
+    double xs[37][TAPE_BS];
+    double gs[37][TAPE_BS];
+};
 
 // x -> E = poly(x), g = dE/dx.  Must be called by ALL threads of a TAPE_BS-wide CTA (it contains barriers).
 __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, double (&x)[36], double (&g)[36], double& E, SymSmem& sm)
@@ -39,7 +44,7 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
     tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
     auto stage = [&](int k) {
         const int t0 = c_sym_chunks3b[k][2], n = c_sym_chunks3b[k + 1][2] - t0;      // both even: 16-byte granules
-        const unsigned dst = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
+        const unsigned dst = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
         for (int i = 2 * tid; i < n; i += 2 * TAPE_BS) tape_cp_async16(dst + 8 * i, tape + t0 + i);
         tape_cp_commit();
     };
@@ -53,7 +58,7 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
             tape_cp_wait<0>();
         }
         __syncthreads();                                   // chunk k visible to every thread
-        unsigned cp = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
+        unsigned cp = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
         const unsigned row1 = c_sym_chunks3b[k + 1][1];
         SYM_ROW_DECL
         SYM_ROW_FETCH(c_sym_chunks3b[k][1])

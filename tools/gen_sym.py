@@ -30,6 +30,7 @@ import numpy as np
 import gen_poly as G
 
 CHUNK = 2048
+DISPATCH = os.environ.get("SYM_DISPATCH", "if")
 NV = 36
 UNIT = NV
 # atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
@@ -224,11 +225,18 @@ def emit(rows, shapes, vps, ahead, nsum):
     L.append("#define SYM_ROW_POST %s" % " ".join(
         "e = fma(Tw_%d, p2_%d, e); tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
         % (j, j, j, j, j, j, j, j, j, j) for j in range(K)))
-    L.append("#define SYM%s_ROW_SWITCH(shape) { \\" % Tg)      # one loop over the super rows, dispatch inside (see tools/gen_fat.py)
-    for s in sorted(shapes):
-        nb = 8 * slots_of(shapes[s])
-        L.append("%sif ((shape) == %d) { %s cp += %d; } \\" % ("else " if s else "", s, body_of[s], nb))
-    L.append("}")
+    if DISPATCH == "switch":      # one loop over the super rows, dispatch inside (see tools/gen_fat.py); jump table instead of a compare tree
+        L.append("#define SYM%s_ROW_SWITCH(shape) switch (shape) { \\" % Tg)
+        for s in sorted(shapes):
+            nb = 8 * slots_of(shapes[s])
+            L.append("case %d: { %s cp += %d; } break; \\" % (s, body_of[s], nb))
+        L.append("default: break; }")
+    else:
+        L.append("#define SYM%s_ROW_SWITCH(shape) { \\" % Tg)
+        for s in sorted(shapes):
+            nb = 8 * slots_of(shapes[s])
+            L.append("%sif ((shape) == %d) { %s cp += %d; } \\" % ("else " if s else "", s, body_of[s], nb))
+        L.append("}")
     return "\n".join(L) + "\n", nfp, len(segs), len(chunks) - 1, len(tape)
 
 
@@ -237,12 +245,17 @@ def main():
     ap.add_argument("--group", default=os.environ.get("SYM_GROUP", "z"), choices=sorted(GROUPS))
     ap.add_argument("--forward", action="store_true", help="trie order = orbit order (default: reversed)")
     ap.add_argument("--repsel", default=os.environ.get("SYM_REPSEL", "max"), choices=["max", "min"])
-    ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "6")))
+    ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "12")))
     ap.add_argument("--nsum", type=int, default=int(os.environ.get("SYM_NSUM", "1")))
+    ap.add_argument("--dispatch", default=DISPATCH, choices=["if", "switch"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("SYM_CHUNK", str(CHUNK))), help="doubles per staged tape chunk")
     ap.add_argument("--out", default=os.path.join(G.OUTD, "sym_3b.h"))
     args = ap.parse_args()
     d = np.load(G.DATA)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    ap_dispatch = args.dispatch
+    globals()["CHUNK"] = args.chunk
+    globals()["DISPATCH"] = ap_dispatch
     rows, shapes, vps = build(d["mono3b"], args.group, not args.forward, args.repsel)
     txt, nfp, nseg, nch, ntape = emit(rows, shapes, vps, args.ahead, args.nsum)
     open(args.out, "w").write(txt)
