@@ -379,6 +379,200 @@ __global__ void k_nrg_eval_ii(int n, int pa, int pb, const double* __restrict__ 
     for (int k = 0; k < 3; ++k) { g1[3 * t + k] = a[k]; g2[3 * t + k] = b[k]; }
 }
 
+// =========================================================================================================
+// 3B ion-water-water (mbnrg-3b-h2o-h2o-<ion>-poly.cpp, poly-3b-h2o-ion-v1x.cpp; driver mbnrg.f90:354-427, do_trimer :781-993 --
+// compiled out in the reference build by `!#define ENABLE_X3B`, mbnrg.f90:4, and therefore a separate, optional entry point here)
+// =========================================================================================================
+constexpr double NRG_R3F_LIST = 7.0;    // mbnrg.f90:135
+constexpr int NRG3_NEAR_CAP = 256;      // waters within 7 A of one ion: ~48 in liquid water
+
+struct Nrg3 {   // parameters of one ion species, order of tools/extract_mbnrg.py PAR_3B
+    double r3i, r3f, k[7], d[7];        // HH_intra OH_intra HH OH OO XH XO
+};
+
+#include "gen/poly3_parts.inc"
+
+// sites 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 X; variable order of mbnrg-3b-h2o-h2o-na-poly.cpp:168-189
+__device__ constexpr int N3A[21] = {1, 4, 0, 0, 3, 3, 1, 1, 2, 2, 0, 0, 3, 3, 0, 6, 6, 6, 6, 6, 6};
+__device__ constexpr int N3B[21] = {2, 5, 1, 2, 4, 5, 4, 5, 4, 5, 4, 5, 1, 2, 3, 1, 2, 4, 5, 0, 3};
+__device__ constexpr int N3K[21] = {0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 5, 5, 5, 5, 6, 6};
+
+// c[21] = w1 (9), w2 (9), x (3) -> E and the gradient on the 7 sites g[21] (kcal/mol, assigned).  The polynomial is OUR shared-prefix
+// Horner schedule (tools/gen_mbnrg.py: 25.5 k FP64 instructions in 24 device functions through a per-thread record).
+__device__ __forceinline__ void h2o_h2o_ion_eval(const Nrg3& P, const double* __restrict__ a, const double (&c)[21], double& E, double (&g)[21])
+{
+    double rec[NRG3_RECORD_DOUBLES];
+    double fac[21];      // -k x / d of every variable
+#pragma unroll
+    for (int n = 0; n < 21; ++n) {
+        const int p = 3 * N3A[n], q = 3 * N3B[n];
+        const double dx = c[p] - c[q], dy = c[p + 1] - c[q + 1], dz = c[p + 2] - c[q + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+        const double xv = exp(-P.k[N3K[n]] * (d - P.d[N3K[n]]));
+        rec[n] = xv;
+        fac[n] = -P.k[N3K[n]] * xv / d;
+    }
+    NRG3_CALL_ALL(rec, a)
+    const double Ep = rec[21];
+    double rab[3], rac[3], rbc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { rab[i] = c[i] - c[9 + i]; rac[i] = c[i] - c[18 + i]; rbc[i] = c[9 + i] - c[18 + i]; }
+    const double drab = sqrt(rab[0] * rab[0] + rab[1] * rab[1] + rab[2] * rab[2]);
+    const double drac = sqrt(rac[0] * rac[0] + rac[1] * rac[1] + rac[2] * rac[2]);
+    const double drbc = sqrt(rbc[0] * rbc[0] + rbc[1] * rbc[1] + rbc[2] * rbc[2]);
+    double gab, gac, gbc;
+    const double sab = switch_fn(drab, P.r3i, P.r3f, gab), sac = switch_fn(drac, P.r3i, P.r3f, gac), sbc = switch_fn(drbc, P.r3i, P.r3f, gbc);
+    const double sw = sab * sac + sab * sbc + sac * sbc;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) g[i] = 0.0;
+#pragma unroll
+    for (int n = 0; n < 21; ++n) {
+        const int p = 3 * N3A[n], q = 3 * N3B[n];
+        const double gg = (rec[22 + n] * sw) * fac[n];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double f = gg * (c[p + i] - c[q + i]);
+            g[p + i] += f;
+            g[q + i] -= f;
+        }
+    }
+    gab *= (sac + sbc) * Ep / drab;
+    gac *= (sab + sbc) * Ep / drac;
+    gbc *= (sab + sac) * Ep / drbc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g[i] += gab * rab[i] + gac * rac[i];
+        g[9 + i] += gbc * rbc[i] - gab * rab[i];
+        g[18 + i] -= gac * rac[i] + gbc * rbc[i];
+    }
+    E = sw * Ep;
+}
+
+// one warp per ion: the waters whose imaged oxygen-ion distance is < r3f (strict, mbnrg.f90:840-842), in index order
+__global__ void k_nrg3_near(int nw, int nions, const double* __restrict__ mono, const double* __restrict__ xyz, int n, CellInfo C,
+                            int* __restrict__ near, int* __restrict__ nnear, int* __restrict__ overflow)
+{
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (k >= nions) return;
+    const double x[3] = {xyz[k], xyz[n + k], xyz[2 * (size_t)n + k]};
+    int cnt = 0;
+    for (int i0 = 0; i0 < nw; i0 += 32) {
+        const int i = i0 + (int)lane;
+        bool in = false;
+        if (i < nw) {
+            double dx = __dsub_rn(mono[i], x[0]), dy = __dsub_rn(mono[(size_t)nw + i], x[1]), dz = __dsub_rn(mono[2 * (size_t)nw + i], x[2]);
+            image_vec(C, dx, dy, dz);
+            in = __dsqrt_rn(norm2_exact(dx, dy, dz)) < NRG_R3F_LIST;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, in);
+        const int pos = cnt + __popc(b & ((1u << lane) - 1u));
+        if (in && pos < NRG3_NEAR_CAP) near[(size_t)k * NRG3_NEAR_CAP + pos] = i;
+        cnt += __popc(b);
+    }
+    if (lane == 0) {
+        if (cnt > NRG3_NEAR_CAP) atomicExch(overflow, 1);
+        nnear[k] = min(cnt, NRG3_NEAR_CAP);
+    }
+}
+
+// exclusive prefix of the trimer counts n (n - 1) / 2 per ion (a few hundred ions at most: one thread)
+__global__ void k_nrg3_offsets(int nions, const int* __restrict__ nnear, long long* __restrict__ off)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    long long t = 0;
+    for (int k = 0; k < nions; ++k) {
+        off[k] = t;
+        t += (long long)nnear[k] * (nnear[k] - 1) / 2;
+    }
+    off[nions] = t;
+}
+
+// one thread per accepted trimer of this rank's contiguous range of the (ion, i, j) list
+__global__ void __launch_bounds__(128) k_nrg3_trimers(int rank, int nranks, int nw, int nions, const double* __restrict__ mono,
+                                                       const double* __restrict__ xyz, int n, const int* __restrict__ list,
+                                                       const int* __restrict__ listions, const int* __restrict__ code, const Nrg3* __restrict__ par,
+                                                       const double* __restrict__ coef, CellInfo C, const int* __restrict__ near,
+                                                       const int* __restrict__ nnear, const long long* __restrict__ off, double* __restrict__ out)
+{
+    const long long T = off[nions], lo = T * rank / nranks, hi = T * (rank + 1) / nranks;
+    for (long long base = lo + (long long)blockIdx.x * blockDim.x; base < hi; base += (long long)gridDim.x * blockDim.x) {
+        const long long t = base + threadIdx.x;
+        double sc[11];
+#pragma unroll
+        for (int q = 0; q < 11; ++q) sc[q] = 0.0;
+        if (t < hi) {
+            int k = 0;
+            while (k + 1 < nions && off[k + 1] <= t) ++k;
+            const long long e = t - off[k];      // pair (p, q), p < q, in the order (0,1), (0,2), ..., (0,n-1), (1,2), ...
+            const int nn = nnear[k];
+            int p = (int)((2.0 * nn - 1.0 - sqrt((2.0 * nn - 1.0) * (2.0 * nn - 1.0) - 8.0 * (double)e)) * 0.5);
+            while ((long long)p * (2 * nn - p - 1) / 2 > e) --p;
+            while ((long long)(p + 1) * (2 * nn - p - 2) / 2 <= e) ++p;
+            const int q = p + 1 + (int)(e - (long long)p * (2 * nn - p - 1) / 2);
+            const int i = near[(size_t)k * NRG3_NEAR_CAP + p], j = near[(size_t)k * NRG3_NEAR_CAP + q];
+            double wi[9], c[21];
+#pragma unroll
+            for (int a = 0; a < 9; ++a) { wi[a] = mono[(size_t)a * nw + i]; c[9 + a] = mono[(size_t)a * nw + j]; }
+            // do_trimer's placement (mbnrg.f90:849-858): water i and the ion next to water j
+            double ax = __dsub_rn(wi[0], c[9]), ay = __dsub_rn(wi[1], c[10]), az = __dsub_rn(wi[2], c[11]);
+            image_vec(C, ax, ay, az);
+            double bx = __dsub_rn(c[9], xyz[k]), by = __dsub_rn(c[10], xyz[n + k]), bz = __dsub_rn(c[11], xyz[2 * (size_t)n + k]);
+            image_vec(C, bx, by, bz);
+            const double ra[3] = {ax, ay, az}, rb[3] = {bx, by, bz};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double o = c[9 + a] + ra[a];
+                c[3 + a] = (wi[3 + a] - wi[a]) + o;
+                c[6 + a] = (wi[6 + a] - wi[a]) + o;
+                c[a] = o;
+                c[18 + a] = c[9 + a] - rb[a];
+            }
+            const int ion = code[k] - 1;
+            double E, g[21];
+            h2o_h2o_ion_eval(par[ion], coef + 1831 * ion, c, E, g);
+            sc[0] = E * MBPOL_ENGUNIT;
+#pragma unroll
+            for (int a = 0; a < 21; ++a) { g[a] *= MBPOL_ENGUNIT; sc[1] += c[a] * g[a]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) s_ += c[3 * m + a] * g[3 * m + b];
+                    sc[2 + 3 * a + b] = -s_;
+                }
+            double* fx = out;
+            double* fy = out + n;
+            double* fz = out + 2 * (size_t)n;
+            const int o1 = list[3 * i] - 1, o2 = list[3 * j] - 1, o3 = listions[k] - 1;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                red_add(fx + o1 + m, -g[3 * m]); red_add(fy + o1 + m, -g[3 * m + 1]); red_add(fz + o1 + m, -g[3 * m + 2]);
+                red_add(fx + o2 + m, -g[9 + 3 * m]); red_add(fy + o2 + m, -g[9 + 3 * m + 1]); red_add(fz + o2 + m, -g[9 + 3 * m + 2]);
+            }
+            red_add(fx + o3, -g[18]); red_add(fy + o3, -g[19]); red_add(fz + o3, -g[20]);
+        }
+        // the reference computes strs(1,2,3,5,6,9) and mirrors (4,7,8) (mbnrg.f90:924-988)
+        sc[2 + 3] = sc[2 + 1]; sc[2 + 6] = sc[2 + 2]; sc[2 + 7] = sc[2 + 5];
+        block_add<11>(sc, out + 3 * (size_t)n);
+        __syncthreads();
+    }
+}
+
+__global__ void k_nrg_eval_3b(int n, int ion, const Nrg3* __restrict__ par, const double* __restrict__ coef, const double* __restrict__ w,
+                              double* __restrict__ E, double* __restrict__ g)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double c[21], e, gg[21];
+    for (int k = 0; k < 21; ++k) c[k] = w[21 * t + k];
+    h2o_h2o_ion_eval(par[ion - 1], coef + 1831 * (ion - 1), c, e, gg);
+    E[t] = e;
+    for (int k = 0; k < 21; ++k) g[21 * t + k] = gg[k];
+}
+
 void host_invert3(const double* a, double* b, double& d)   // invert.f
 {
     b[0] = a[4] * a[8] - a[5] * a[7]; b[1] = a[2] * a[7] - a[1] * a[8]; b[2] = a[1] * a[5] - a[2] * a[4];
@@ -405,6 +599,14 @@ struct mbnrg_b200_handle {
     int2* pairs = nullptr;
     unsigned char* have_ii = nullptr;
     unsigned long long* counters = nullptr;
+    // 3B
+    Nrg3* par3 = nullptr;
+    double* coef3 = nullptr;
+    int *near = nullptr, *nnear = nullptr, *ovf3 = nullptr;
+    long long* off3 = nullptr;
+    long long counts3[2] = {0, 0};
+    float ms3[3] = {0, 0, 0};
+    cudaEvent_t ev3[3] = {nullptr, nullptr, nullptr};
     size_t cap_atoms = 0, cap_scratch = 0;
     std::vector<double> host_out;
     long long counts[3] = {0, 0, 0};
@@ -460,6 +662,16 @@ int mbnrg_b200_init(int nttm2, int nions, const int* ion_code, int device, mbnrg
     NRG_TRY(h, cudaMalloc(&h->code, std::max<size_t>(1, nions) * sizeof(int)));
     NRG_TRY(h, cudaMalloc(&h->pairs, std::max<size_t>(1, (size_t)nions * h->nw) * sizeof(int2)));
     if (nions) NRG_TRY(h, cudaMemcpy(h->code, ion_code, nions * sizeof(int), cudaMemcpyHostToDevice));
+    static_assert(sizeof(Nrg3) == 16 * sizeof(double), "3B parameter layout");
+    NRG_TRY(h, cudaMalloc(&h->par3, sizeof(MBNRG_PAR_3B)));
+    NRG_TRY(h, cudaMalloc(&h->coef3, sizeof(MBNRG_COEF_3B)));
+    NRG_TRY(h, cudaMemcpy(h->par3, MBNRG_PAR_3B, sizeof(MBNRG_PAR_3B), cudaMemcpyHostToDevice));
+    NRG_TRY(h, cudaMemcpy(h->coef3, MBNRG_COEF_3B, sizeof(MBNRG_COEF_3B), cudaMemcpyHostToDevice));
+    NRG_TRY(h, cudaMalloc(&h->near, std::max<size_t>(1, nions) * NRG3_NEAR_CAP * sizeof(int)));
+    NRG_TRY(h, cudaMalloc(&h->nnear, std::max<size_t>(1, nions) * sizeof(int)));
+    NRG_TRY(h, cudaMalloc(&h->off3, (std::max<size_t>(1, nions) + 1) * sizeof(long long)));
+    NRG_TRY(h, cudaMalloc(&h->ovf3, sizeof(int)));
+    for (auto& e : h->ev3) NRG_TRY(h, cudaEventCreate(&e));
     return MBPOL_B200_OK;
 }
 
@@ -469,9 +681,12 @@ int mbnrg_b200_fini(mbnrg_b200_handle* h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : {(void*)h->xyz, (void*)h->mono, (void*)h->out, (void*)h->coef, (void*)h->coef_ii, (void*)h->par_ii, (void*)h->scratch,
-                    (void*)h->par, (void*)h->list, (void*)h->listions, (void*)h->code, (void*)h->pairs, (void*)h->have_ii, (void*)h->counters})
+                    (void*)h->par, (void*)h->list, (void*)h->listions, (void*)h->code, (void*)h->pairs, (void*)h->have_ii, (void*)h->counters,
+                    (void*)h->par3, (void*)h->coef3, (void*)h->near, (void*)h->nnear, (void*)h->off3, (void*)h->ovf3})
         if (p) cudaFree(p);
     for (auto e : h->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto e : h->ev3)
         if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -586,6 +801,114 @@ int mbnrg_b200_kernel_times(const mbnrg_b200_handle* h, float ms[4], int* launch
     if (!h || !ms) return MBPOL_B200_EINVAL;
     for (int k = 0; k < 4; ++k) ms[k] = h->ms[k];
     if (launches) *launches = h->launches;
+    return MBPOL_B200_OK;
+}
+
+// The 3B ion-water-water term (optional: the reference build has it compiled out, mbnrg.f90:4).  Same conventions as
+// mbnrg_b200_forces: forces, *eng3, *vir3 and stress[9] are accumulated into; rank r of nranks evaluates the contiguous range
+// [T r/N, T (r+1)/N) of the accepted (ion, water i < water j) trimers.
+int mbnrg_b200_forces_3b(mbnrg_b200_handle* h, int imcon, const double* cell, int nttm2, const int* listttm2, int nions, const int* listions,
+                         int mxatms, const double* xxx, const double* yyy, const double* zzz, double* fxx, double* fyy, double* fzz,
+                         double* eng3, double* vir3, double* stress)
+{
+    if (!h) return MBPOL_B200_EINVAL;
+    if (imcon < 1 || imcon > 3 || !cell || nttm2 != h->nttm2 || nions != h->nions || mxatms < nions || !xxx || !yyy || !zzz || !fxx || !fyy ||
+        !fzz || !eng3 || !vir3 || !stress || (nttm2 && !listttm2) || (nions && !listions)) {
+        h->err = "mbnrg_b200_forces_3b: invalid argument (imcon must be 1, 2 or 3; nttm2 / nions must match init)";
+        return MBPOL_B200_EINVAL;
+    }
+    NRG_TRY(h, cudaSetDevice(h->device));
+    const size_t n = mxatms;
+    if (n > h->cap_atoms) {
+        if (h->xyz) cudaFree(h->xyz);
+        if (h->out) cudaFree(h->out);
+        h->xyz = h->out = nullptr;
+        NRG_TRY(h, cudaMalloc(&h->xyz, 3 * n * sizeof(double)));
+        NRG_TRY(h, cudaMalloc(&h->out, (3 * n + NSC) * sizeof(double)));
+        h->cap_atoms = n;
+    }
+    CellInfo C;
+    C.imcon = imcon;
+    std::copy(cell, cell + 9, C.cell);
+    double det;
+    host_invert3(cell, C.rcell, det);
+    C.a1 = 1.0 / cell[0]; C.b1 = 1.0 / cell[4]; C.c1 = 1.0 / cell[8];
+    cudaStream_t s = h->stream;
+    const int nw = h->nw;
+    NRG_TRY(h, cudaMemcpyAsync(h->xyz, xxx, n * 8, cudaMemcpyHostToDevice, s));
+    NRG_TRY(h, cudaMemcpyAsync(h->xyz + n, yyy, n * 8, cudaMemcpyHostToDevice, s));
+    NRG_TRY(h, cudaMemcpyAsync(h->xyz + 2 * n, zzz, n * 8, cudaMemcpyHostToDevice, s));
+    if (nttm2) NRG_TRY(h, cudaMemcpyAsync(h->list, listttm2, (size_t)nttm2 * 4, cudaMemcpyHostToDevice, s));
+    if (nions) NRG_TRY(h, cudaMemcpyAsync(h->listions, listions, (size_t)nions * 4, cudaMemcpyHostToDevice, s));
+    NRG_TRY(h, cudaMemsetAsync(h->out, 0, (3 * n + NSC) * sizeof(double), s));
+    NRG_TRY(h, cudaMemsetAsync(h->ovf3, 0, sizeof(int), s));
+    NRG_TRY(h, cudaEventRecord(h->ev3[0], s));
+    long long off_end = 0;
+    int ovf = 0;
+    if (nw > 1 && nions) {
+        k_nrg_gather<<<(nw + 127) / 128, 128, 0, s>>>(nw, h->list, h->xyz, h->xyz + n, h->xyz + 2 * n, C, h->mono);
+        k_nrg3_near<<<(nions * 32 + 127) / 128, 128, 0, s>>>(nw, nions, h->mono, h->xyz, (int)n, C, h->near, h->nnear, h->ovf3);
+        k_nrg3_offsets<<<1, 32, 0, s>>>(nions, h->nnear, h->off3);
+        NRG_TRY(h, cudaEventRecord(h->ev3[1], s));
+        // latency-sized workload (a few 1e4 trimers of 25 k FP64 instructions): the grid is a fixed multiple of the SM count and the
+        // kernel strides over its range, so no list length has to come back to the host first
+        k_nrg3_trimers<<<148 * 4, 128, 0, s>>>(h->rank, h->nranks, nw, nions, h->mono, h->xyz, (int)n, h->list, h->listions, h->code, h->par3,
+                                               h->coef3, C, h->near, h->nnear, h->off3, h->out);
+        NRG_TRY(h, cudaMemcpyAsync(&off_end, h->off3 + nions, 8, cudaMemcpyDeviceToHost, s));
+        NRG_TRY(h, cudaMemcpyAsync(&ovf, h->ovf3, 4, cudaMemcpyDeviceToHost, s));
+    } else {
+        NRG_TRY(h, cudaEventRecord(h->ev3[1], s));
+    }
+    NRG_TRY(h, cudaEventRecord(h->ev3[2], s));
+    NRG_TRY(h, cudaGetLastError());
+    h->host_out.resize(3 * n + NSC);
+    NRG_TRY(h, cudaMemcpyAsync(h->host_out.data(), h->out, (3 * n + NSC) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NRG_TRY(h, cudaStreamSynchronize(s));
+    if (ovf) { h->err = "more than NRG3_NEAR_CAP waters within 7 A of an ion: unphysical density"; return MBPOL_B200_ECAPACITY; }
+    h->counts3[0] = off_end;
+    h->counts3[1] = off_end * (h->rank + 1) / h->nranks - off_end * h->rank / h->nranks;
+    cudaEventElapsedTime(&h->ms3[0], h->ev3[0], h->ev3[1]);
+    cudaEventElapsedTime(&h->ms3[1], h->ev3[1], h->ev3[2]);
+    cudaEventElapsedTime(&h->ms3[2], h->ev3[0], h->ev3[2]);
+    const double* o = h->host_out.data();
+    for (size_t i = 0; i < n; ++i) {
+        fxx[i] += o[i];
+        fyy[i] += o[n + i];
+        fzz[i] += o[2 * n + i];
+    }
+    *eng3 += o[3 * n];
+    *vir3 += o[3 * n + 1];
+    for (int k = 0; k < 9; ++k) stress[k] += o[3 * n + 2 + k];
+    return MBPOL_B200_OK;
+}
+
+int mbnrg_b200_counts_3b(const mbnrg_b200_handle* h, long long counts[2], float ms[3])
+{
+    if (!h || !counts) return MBPOL_B200_EINVAL;
+    counts[0] = h->counts3[0]; counts[1] = h->counts3[1];
+    if (ms) for (int k = 0; k < 3; ++k) ms[k] = h->ms3[k];
+    return MBPOL_B200_OK;
+}
+
+int mbnrg_b200_eval_h2o_h2o_ion(mbnrg_b200_handle* h, int ion, int n, const double* w /* [n][21]: w1, w2, x */, double* E, double* g /* [n][21] */)
+{
+    if (!h || ion < 1 || ion > MBNRG_NIONS || n < 0 || !w || !E || !g) return MBPOL_B200_EINVAL;
+    if (n == 0) return MBPOL_B200_OK;
+    NRG_TRY(h, cudaSetDevice(h->device));
+    const size_t need = (size_t)n * 43;
+    if (need > h->cap_scratch) {
+        if (h->scratch) cudaFree(h->scratch);
+        h->scratch = nullptr;
+        NRG_TRY(h, cudaMalloc(&h->scratch, need * sizeof(double)));
+        h->cap_scratch = need;
+    }
+    double *dw = h->scratch, *dE = dw + (size_t)n * 21, *dg = dE + n;
+    NRG_TRY(h, cudaMemcpyAsync(dw, w, (size_t)n * 21 * 8, cudaMemcpyHostToDevice, h->stream));
+    k_nrg_eval_3b<<<(n + 127) / 128, 128, 0, h->stream>>>(n, ion, h->par3, h->coef3, dw, dE, dg);
+    NRG_TRY(h, cudaGetLastError());
+    NRG_TRY(h, cudaMemcpyAsync(E, dE, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    NRG_TRY(h, cudaMemcpyAsync(g, dg, (size_t)n * 21 * 8, cudaMemcpyDeviceToHost, h->stream));
+    NRG_TRY(h, cudaStreamSynchronize(h->stream));
     return MBPOL_B200_OK;
 }
 

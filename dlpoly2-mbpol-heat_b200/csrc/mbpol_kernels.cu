@@ -11,7 +11,8 @@
 // Scatter: FP64 red.global.add into the packed output buffer; scalars are block-reduced first.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: the library is bound at run time (nccl_api below)
 
 #include <algorithm>
 #include <cmath>
@@ -135,18 +136,16 @@ __global__ void k_cell_fill(int nw, const int* __restrict__ cell_id, const int* 
 // ---------------------------------------------------------------------------------------------------------
 // The cell fill order comes from atomics; sorting every cell's (short) member list makes the neighbour rows -- and
 // therefore the lists and the per-rank shards cut out of them -- identical on every GPU and from call to call.
-__global__ void k_sort_cells(int ncells, const int* __restrict__ cell_start, int* __restrict__ sorted)
+__global__ void k_sort_cells(int nw, const int* __restrict__ cell_id, const int* __restrict__ cell_start, const int* __restrict__ unsorted,
+                             int* __restrict__ sorted)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    int* row = sorted + cell_start[c];
-    const int n = cell_start[c + 1] - cell_start[c];
-    for (int a = 1; a < n; ++a) {
-        const int v = row[a];
-        int b = a - 1;
-        while (b >= 0 && row[b] > v) { row[b + 1] = row[b]; --b; }
-        row[b + 1] = v;
-    }
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per water: its rank = members of its cell with a smaller index
+    if (m >= nw) return;
+    const int c = cell_id[m];
+    const int p0 = cell_start[c], p1 = cell_start[c + 1];
+    int rank = 0;
+    for (int p = p0; p < p1; ++p) rank += unsorted[p] < m;
+    sorted[p0 + rank] = m;
 }
 
 // One WARP per water of this rank's range [w0, w0 + nown): the lanes share the scan of the 27 surrounding cells; accepted
@@ -237,7 +236,7 @@ __device__ __forceinline__ bool within_r3f(int nw, const double* __restrict__ mo
 // load-balancing weight (4 x trimers + dimers) for the next step's shard boundaries.
 template <bool FILL>
 __global__ void k_trimers_enum(int w0, int nown, int nw, const double* __restrict__ mono, CellInfo C, const int* __restrict__ nb3,
-                               const int* __restrict__ n3, const int* __restrict__ n2, long long* __restrict__ cnt, int* __restrict__ weight,
+                               const int* __restrict__ n3, const int* __restrict__ n2, long long* __restrict__ cnt, double* __restrict__ weight,
                                const long long* __restrict__ off, int* __restrict__ trimers, long long cap, int* __restrict__ overflow)
 {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per centre
@@ -281,7 +280,7 @@ __global__ void k_trimers_enum(int w0, int nown, int nw, const double* __restric
     }
     if (!FILL && lane == 0) {
         cnt[t] = k;
-        weight[c] = (int)(4 * k) + n2[t];
+        weight[c] = (double)(4 * k + n2[t]);
     }
 }
 
@@ -541,7 +540,7 @@ struct mbpol_b200_handle {
     Grid G;
     int ncells = 0;
     DevBuf<double> xyz, vel, mono, out, rec, rec2;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
-    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur, weight;
+    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, unsorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur;
     DevBuf<unsigned> inc, inc2;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll, counts;
@@ -554,7 +553,8 @@ struct mbpol_b200_handle {
     int w0 = 0, nown = 0;
     long long est_nd = -1, est_nt = -1;        // counts of the previous step: sizes and grids of this one (no host round trip)
     struct HostBack { long long counts[4]; double tail[3]; int flag; int pad; } *back = nullptr;     // pinned: read back once per step
-    int* host_weight = nullptr;                // pinned: per-water load-balancing weights of the previous step (all ranks)
+    double* host_weight_d = nullptr;           // pinned: per-water load-balancing weights of the previous step (all ranks)
+    std::vector<int> host_weight;
     bool have_weight = false;
     ncclComm_t comm = nullptr;
     int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
@@ -565,6 +565,8 @@ struct mbpol_b200_handle {
     size_t chunk() const { const size_t c = (atom_count() + nranks - 1) / nranks; return (c + 1) & ~(size_t)1; }
     size_t scal_offset() const { return chunk() * nranks; }
     size_t out_count() const { return scal_offset() + (size_t)NSCAL * nbeads; }
+    size_t weight_offset() const { return out_count(); }        // per-water weights of this step, as doubles, right behind the scalars
+    size_t out_alloc() const { return out_count() + (size_t)nw + 2; }
     OutPtrs views()
     {
         OutPtrs O;
@@ -599,11 +601,43 @@ int scan_int(mbpol_b200_handle* h, const int* in, int* out, int n)
     return 0;
 }
 
+// NCCL is bound lazily with dlopen / dlsym at the first communicator call, not at load time: a process that imports PyTorch AFTER
+// this library must still get PyTorch's own (newer) libnccl.so.2 -- two copies under one SONAME cannot coexist.  An NCCL that is
+// already in the process (RTLD_NOLOAD) is reused, otherwise the system library is opened.
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclReduceScatter) ReduceScatter = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return;
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(lib, "ncclReduceScatter"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.ReduceScatter && api.AllReduce && api.GetErrorString;
+    });
+    return api;
+}
+
 #define NCCL_TRY(h, call)                                                                                   \
     do {                                                                                                    \
         ncclResult_t r_ = (call);                                                                           \
         if (r_ != ncclSuccess) {                                                                            \
-            (h)->err = std::string(#call) + ": " + ncclGetErrorString(r_);                                  \
+            (h)->err = std::string(#call) + ": " + nccl_api().GetErrorString(r_);                                  \
             return MBPOL_B200_ECUDA;                                                                        \
         }                                                                                                   \
     } while (0)
@@ -670,11 +704,11 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     if (!h) return MBPOL_B200_EINVAL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->comm) ncclCommDestroy(h->comm);
+    if (h->comm) nccl_api().CommDestroy(h->comm);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->back) cudaFreeHost(h->back);
-    if (h->host_weight) cudaFreeHost(h->host_weight);
+    if (h->host_weight_d) cudaFreeHost(h->host_weight_d);
     for (cudaEvent_t e : h->dl_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -699,7 +733,8 @@ int mbpol_b200_comm_unique_id(void* id)
 {
     static_assert(sizeof(ncclUniqueId) == MBPOL_B200_UNIQUE_ID_BYTES, "NCCL unique id size");
     if (!id) return MBPOL_B200_EINVAL;
-    return ncclGetUniqueId(reinterpret_cast<ncclUniqueId*>(id)) == ncclSuccess ? MBPOL_B200_OK : MBPOL_B200_ECUDA;
+    if (!nccl_api().ok) return MBPOL_B200_ECUDA;
+    return nccl_api().GetUniqueId(reinterpret_cast<ncclUniqueId*>(id)) == ncclSuccess ? MBPOL_B200_OK : MBPOL_B200_ECUDA;
 }
 
 int mbpol_b200_comm_init(mbpol_b200_handle* h, int rank, int nranks, const void* id)
@@ -708,7 +743,8 @@ int mbpol_b200_comm_init(mbpol_b200_handle* h, int rank, int nranks, const void*
     CUDA_TRY(h, cudaSetDevice(h->device));
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof(uid));
-    NCCL_TRY(h, ncclCommInitRank(&h->comm, nranks, uid, rank));
+    if (!nccl_api().ok) { h->err = "libnccl.so.2 not found (or too old): the in-library reduction needs NCCL"; return MBPOL_B200_ECUDA; }
+    NCCL_TRY(h, nccl_api().CommInitRank(&h->comm, nranks, uid, rank));
     h->rank = rank; h->nranks = nranks;
     h->est_nd = h->est_nt = -1; h->have_weight = false;
     h->reduce_mode = nranks > 1 ? 2 : 0;
@@ -811,24 +847,24 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     // shard of this rank
     {
         std::vector<int> bounds(h->nranks + 1);
-        mbpol_b200_shard_bounds(nw, h->nranks, (h->nranks > 1 && h->have_weight) ? h->host_weight : nullptr, bounds.data());
+        mbpol_b200_shard_bounds(nw, h->nranks, (h->nranks > 1 && h->have_weight) ? h->host_weight.data() : nullptr, bounds.data());
         h->w0 = bounds[h->rank];
         h->nown = bounds[h->rank + 1] - bounds[h->rank];
     }
     const int w0 = h->w0, nown = h->nown;
     const int gb = (nw + TB - 1) / TB, go = (nown + TB - 1) / TB;
     CUDA_TRY(h, h->mono.reserve(9 * (size_t)nw));
-    CUDA_TRY(h, h->out.reserve(h->out_count()));
-    CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw));
+    CUDA_TRY(h, h->out.reserve(h->out_alloc()));
+    CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw)); CUDA_TRY(h, h->unsorted.reserve(nw));
     CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
     CUDA_TRY(h, h->nb2.reserve((size_t)std::max(nown, 1) * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)std::max(nown, 1) * NB3_CAP));
     CUDA_TRY(h, h->n2.reserve(nown + 1)); CUDA_TRY(h, h->n3.reserve(nown + 1)); CUDA_TRY(h, h->flag.reserve(1));
     CUDA_TRY(h, h->off2.reserve(nown + 1)); CUDA_TRY(h, h->off3.reserve(nown + 1)); CUDA_TRY(h, h->cnt3.reserve(nown + 1));
-    CUDA_TRY(h, h->n2ll.reserve(nown + 1)); CUDA_TRY(h, h->counts.reserve(4)); CUDA_TRY(h, h->weight.reserve(nw + 1));
+    CUDA_TRY(h, h->n2ll.reserve(nown + 1)); CUDA_TRY(h, h->counts.reserve(4));
     CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
 
     CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
-    CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_count() * 8, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_alloc() * 8, s));
     OutPtrs O = h->views();
     h->back->flag = 0;
     for (long long& c : h->back->counts) c = 0;
@@ -842,18 +878,17 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, cudaMemsetAsync(h->cell_cnt.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->cell_fill.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->flag.p, 0, 4, s));
-    CUDA_TRY(h, cudaMemsetAsync(h->weight.p, 0, (size_t)(nw + 1) * 4, s));
     k_gather_image<<<gb, TB, 0, s>>>(nw, h->list.p, h->xyz.p, h->xyz.p + n, h->xyz.p + 2 * n, h->C, h->mono.p);
     k_cell_index<<<gb, TB, 0, s>>>(nw, h->mono.p, h->G, h->cell_id.p, h->cell_cnt.p);
     if (int rc = scan_int(h, h->cell_cnt.p, h->cell_cnt.p, h->ncells + 1)) return rc;   // in-place exclusive scan -> cell_start
-    k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->sorted.p);
-    k_sort_cells<<<(h->ncells + TB - 1) / TB, TB, 0, s>>>(h->ncells, h->cell_cnt.p, h->sorted.p);
+    k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->unsorted.p);
+    k_sort_cells<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->unsorted.p, h->sorted.p);
     h->launches += 6;
     const int gw = (int)(((size_t)std::max(nown, 1) * 32 + TB - 1) / TB);      // one warp per owned water
     if (nown > 0) {
         k_neighbours<<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
         k_widen<<<go, TB, 0, s>>>(nown, h->n2.p, h->n2ll.p);
-        k_trimers_enum<false><<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->nb3.p, h->n3.p, h->n2.p, h->cnt3.p, h->weight.p, nullptr, nullptr, 0, h->flag.p);
+        k_trimers_enum<false><<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->nb3.p, h->n3.p, h->n2.p, h->cnt3.p, h->out.p + h->weight_offset(), nullptr, nullptr, 0, h->flag.p);
         h->launches += 3;
     }
     CUDA_TRY(h, cudaMemsetAsync(h->n2ll.p + nown, 0, 8, s));
@@ -941,13 +976,12 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     // ---- reduction over the ranks (NCCL over NVLink, on this stream): forces, per-atom arrays, scalars, weights -------------
     if (h->reduce_mode && h->comm) {
         if (h->reduce_mode == 2) {
-            NCCL_TRY(h, ncclReduceScatter(h->out.p, h->out.p + (size_t)h->rank * h->chunk(), h->chunk(), ncclDouble, ncclSum, h->comm, s));
-            NCCL_TRY(h, ncclAllReduce(O.scal, O.scal, (size_t)NSCAL * h->nbeads, ncclDouble, ncclSum, h->comm, s));
+            NCCL_TRY(h, nccl_api().ReduceScatter(h->out.p, h->out.p + (size_t)h->rank * h->chunk(), h->chunk(), ncclDouble, ncclSum, h->comm, s));
+            NCCL_TRY(h, nccl_api().AllReduce(O.scal, O.scal, (size_t)NSCAL * h->nbeads + nw, ncclDouble, ncclSum, h->comm, s));      // scalars + weights
         } else {
-            NCCL_TRY(h, ncclAllReduce(h->out.p, h->out.p, h->out_count(), ncclDouble, ncclSum, h->comm, s));
+            NCCL_TRY(h, nccl_api().AllReduce(h->out.p, h->out.p, h->out_count() + nw, ncclDouble, ncclSum, h->comm, s));
         }
-        NCCL_TRY(h, ncclAllReduce(h->weight.p, h->weight.p, (size_t)nw, ncclInt, ncclSum, h->comm, s));
-        h->launches += 3;
+        h->launches += 2;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[4], s));
     // ---- the one read-back of the step: counts, overflow flag, weights ---------------------------------------------------
@@ -955,8 +989,8 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, cudaMemcpyAsync(&h->back->flag, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(h->back->tail, O.scal + S_ND, 24, cudaMemcpyDeviceToHost, s));      // S_ND, S_NT, S_OVF
     if (h->nranks > 1) {
-        if (!h->host_weight) CUDA_TRY(h, cudaMallocHost(&h->host_weight, (size_t)(nw + 1) * 4));
-        CUDA_TRY(h, cudaMemcpyAsync(h->host_weight, h->weight.p, (size_t)nw * 4, cudaMemcpyDeviceToHost, s));
+        if (!h->host_weight_d) CUDA_TRY(h, cudaMallocHost(&h->host_weight_d, (size_t)(nw + 1) * 8));
+        CUDA_TRY(h, cudaMemcpyAsync(h->host_weight_d, h->out.p + h->weight_offset(), (size_t)nw * 8, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -970,6 +1004,10 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     // box totals: the counts rode through the reduction in the scalar block (bead 0); without one, the shard is all this rank knows
     h->nd_total = (long long)(h->back->tail[0] + 0.5); h->nt_total = (long long)(h->back->tail[1] + 0.5);
     h->have_weight = h->nranks > 1 && h->reduce_mode && h->comm;      // without a communicator the weights of the other ranks are unknown
+    if (h->have_weight) {
+        h->host_weight.resize(nw);
+        for (int i = 0; i < nw; ++i) h->host_weight[i] = (int)h->host_weight_d[i];
+    }
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);

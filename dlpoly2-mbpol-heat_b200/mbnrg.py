@@ -35,6 +35,7 @@ def _lib():
         lib.mbnrg_b200_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.mbnrg_b200_counts.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         lib.mbnrg_b200_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), _ip]
+        lib.mbnrg_b200_counts_3b.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
         lib._nrg_ready = True
     return lib
 
@@ -119,4 +120,41 @@ def run_ion_box(h, box):
     out["stress"] = np.zeros(9)
     out.update(mbnrg_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"], box["xxx"],
                             box["yyy"], box["zzz"], out["fxx"], out["fyy"], out["fzz"], out["stress"]))
+    return out
+
+
+# ---- 3B ion-water-water (optional: compiled out in the reference build, mbnrg.f90:4) -----------------------------------------
+def mbnrg_forces_3b(h, imcon, cell, nttm2, listttm2, nions, listions, xxx, yyy, zzz, fxx, fyy, fzz, stress, engsrp=0.0, virsrp=0.0):
+    """The 3B part of mbnrg_forces (mbnrg.f90:354-427): accumulates into fxx/fyy/fzz/stress, returns eng3 / vir3 and the updated sums."""
+    e, v = C.c_double(0.0), C.c_double(0.0)
+    cell = np.ascontiguousarray(cell, dtype=np.float64)
+    rc = _lib().mbnrg_b200_forces_3b(h.ptr, C.c_int(int(imcon)), _p(cell), C.c_int(int(nttm2)), _p(listttm2, np.int32), C.c_int(int(nions)),
+                                     _p(listions, np.int32), C.c_int(len(xxx)), _p(xxx), _p(yyy), _p(zzz), _p(fxx), _p(fyy), _p(fzz),
+                                     C.byref(e), C.byref(v), _p(stress))
+    _check(h, rc, "mbnrg_b200_forces_3b")
+    return {"eng3": e.value, "vir3": v.value, "engsrp": engsrp + e.value, "virsrp": virsrp + v.value, "stress": stress}
+
+
+def mbnrg_counts_3b(h):
+    c, ms = (C.c_longlong * 2)(), (C.c_float * 3)()
+    _check(h, _lib().mbnrg_b200_counts_3b(h.ptr, c, ms), "mbnrg_b200_counts_3b")
+    return {"ntrimers": int(c[0]), "nshard": int(c[1]), "list_ms": float(ms[0]), "eval_ms": float(ms[1]), "total_ms": float(ms[2])}
+
+
+def mbnrg_eval_h2o_h2o_ion(h, ion, w):
+    """Batched mbnrg_3b_h2o_h2o_<ion>_poly_: w [n, 21] = (w1, w2, x) -> E[n] (kcal/mol), g[n, 21]."""
+    w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1, 21)
+    n = len(w)
+    E, g = np.zeros(n), np.zeros((n, 21))
+    _check(h, _lib().mbnrg_b200_eval_h2o_h2o_ion(h.ptr, C.c_int(int(ion)), C.c_int(n), _p(w), _p(E), _p(g)), "mbnrg_b200_eval_h2o_h2o_ion")
+    return E, g
+
+
+def run_ion_box_3b(h, box):
+    n = int(box["mxatms"])
+    out = {k: np.zeros(n) for k in ("fxx", "fyy", "fzz")}
+    st = np.zeros(9)
+    r = mbnrg_forces_3b(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"], box["xxx"], box["yyy"],
+                        box["zzz"], out["fxx"], out["fyy"], out["fzz"], st)
+    out.update(r)
     return out

@@ -212,6 +212,88 @@ double eval_ion_ion(int a, int b, const double* w, const double* x, double* g1, 
     return sw * Ep;
 }
 
+
+// ---- 3B ion-water-water (mbnrg-3b-h2o-h2o-<ion>-poly.cpp) -----------------------------------------------------------
+typedef void (*refpoly3_t)(const double*, const double*, const double*, double*, double*, double*, double*);
+refpoly3_t ref_3b[9];
+
+// E = sum_m a_k prod x_v, g = dE/dx from the raw monomial table of poly-3b-h2o-ion-v1x.cpp (21 variables, degree <= 5)
+double poly_3b(const double* a, const double* x, double* g)
+{
+    double E = 0.0;
+    for (int v = 0; v < 21; ++v) g[v] = 0.0;
+    for (int m = 0; m < ORC_NRG_NMONO3; ++m) {
+        const short* r = ORC_NRG_MONO3[m];
+        int n = 0;
+        while (n < 5 && r[1 + n] >= 0) ++n;
+        double p = a[r[0]];
+        for (int i = 0; i < n; ++i) p *= x[r[1 + i]];
+        E += p;
+        for (int i = 0; i < n; ++i) {
+            double q = a[r[0]];
+            for (int j = 0; j < n; ++j)
+                if (j != i) q *= x[r[1 + j]];
+            g[r[1 + i]] += q;
+        }
+    }
+    return E;
+}
+
+// x3b_h2o_ion_v2x_p::operator() (mbnrg-3b-h2o-h2o-na-poly.cpp:149-305): sites 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 X;
+// 21 variables exp(-k (d - d0)) (:168-189); s = sab sac + sab sbc + sac sbc on |Oa-Ob|, |Oa-X|, |Ob-X| (:196-219);
+// gradients are ACCUMULATED into g1, g2, g3 (:28-41, 61-78); parameters in the order of tools/extract_mbnrg.py PAR_3B
+const int V3N_A[21] = {1, 4, 0, 0, 3, 3, 1, 1, 2, 2, 0, 0, 3, 3, 0, 6, 6, 6, 6, 6, 6};
+const int V3N_B[21] = {2, 5, 1, 2, 4, 5, 4, 5, 4, 5, 4, 5, 1, 2, 3, 1, 2, 4, 5, 0, 3};
+const int V3N_K[21] = {0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 5, 5, 5, 5, 6, 6};   // HH_intra OH_intra HH OH OO XH XO
+double eval_h2o_h2o_ion(int ion, const double* w1, const double* w2, const double* x, double* g1, double* g2, double* g3)
+{
+    const double* P = ORC_NRG_PAR_3B + 16 * (ion - 1);
+    const double r3i = P[0], r3f = P[1];
+    const double* kk = P + 2;     // 7 k's
+    const double* dd = P + 9;     // 7 d0's
+    double c[21];
+    for (int i = 0; i < 9; ++i) { c[i] = w1[i]; c[9 + i] = w2[i]; }
+    for (int i = 0; i < 3; ++i) c[18 + i] = x[i];
+    double xi[21], g[21], dx[21][3], dist[21];
+    for (int n = 0; n < 21; ++n) {
+        const int a = 3 * V3N_A[n], b = 3 * V3N_B[n];
+        for (int i = 0; i < 3; ++i) dx[n][i] = c[a + i] - c[b + i];
+        dist[n] = std::sqrt(dx[n][0] * dx[n][0] + dx[n][1] * dx[n][1] + dx[n][2] * dx[n][2]);
+        xi[n] = std::exp(-kk[V3N_K[n]] * (dist[n] - dd[V3N_K[n]]));
+    }
+    double E = poly_3b(ORC_NRG_COEF_3B + 1831 * (ion - 1), xi, g);
+    double rab[3], rac[3], rbc[3], drab = 0, drac = 0, drbc = 0;
+    for (int i = 0; i < 3; ++i) {
+        rab[i] = c[i] - c[9 + i]; drab += rab[i] * rab[i];
+        rac[i] = c[i] - c[18 + i]; drac += rac[i] * rac[i];
+        rbc[i] = c[9 + i] - c[18 + i]; drbc += rbc[i] * rbc[i];
+    }
+    drab = std::sqrt(drab); drac = std::sqrt(drac); drbc = std::sqrt(drbc);
+    double gab, gac, gbc;
+    const double sab = f_switch(drab, r3i, r3f, gab), sac = f_switch(drac, r3i, r3f, gac), sbc = f_switch(drbc, r3i, r3f, gbc);
+    const double sw = sab * sac + sab * sbc + sac * sbc;
+    double gr[21];
+    for (int i = 0; i < 21; ++i) gr[i] = 0.0;
+    for (int n = 0; n < 21; ++n) {
+        const double gg = -kk[V3N_K[n]] * (g[n] * sw) * xi[n] / dist[n];
+        for (int i = 0; i < 3; ++i) {
+            gr[3 * V3N_A[n] + i] += gg * dx[n][i];
+            gr[3 * V3N_B[n] + i] -= gg * dx[n][i];
+        }
+    }
+    gab *= (sac + sbc) * E / drab;
+    gac *= (sab + sbc) * E / drac;
+    gbc *= (sab + sac) * E / drbc;
+    for (int i = 0; i < 3; ++i) {
+        gr[i] += gab * rab[i] + gac * rac[i];
+        gr[9 + i] += gbc * rbc[i] - gab * rab[i];
+        gr[18 + i] -= gac * rac[i] + gbc * rbc[i];
+    }
+    for (int i = 0; i < 9; ++i) { g1[i] += gr[i]; g2[i] += gr[9 + i]; }
+    for (int i = 0; i < 3; ++i) g3[i] += gr[18 + i];
+    return E * sw;
+}
+
 }  // namespace
 
 extern "C" {
@@ -226,6 +308,8 @@ int oracle_mbnrg_load_reference(const char* path)
         snprintf(name, sizeof name, "mbnrg_2b_h2o_%s_poly_", ION[i]);
         ref_hi[i] = (refpoly_t)dlsym(ref_handle, name);
         if (!ref_hi[i]) return 2;
+        snprintf(name, sizeof name, "mbnrg_3b_h2o_h2o_%s_poly_", ION[i]);
+        ref_3b[i] = (refpoly3_t)dlsym(ref_handle, name);      // absent in a 2B-only reference build: the 3B calls then use the restatement
         for (int j = 0; j < 9; ++j) {
             snprintf(name, sizeof name, "mbnrg_2b_%s_%s_poly_", ION[i], ION[j]);
             ref_ii[i][j] = (refpoly_t)dlsym(ref_handle, name);
@@ -363,6 +447,94 @@ int oracle_mbnrg_forces(int use_ref, int rank, int nranks, int imcon, const doub
         counts[1] = c1;
         counts[2] = c2;
     }
+    return 0;
+}
+
+
+double oracle_mbnrg_poly3b(const double* a, const double* x, double* g) { return poly_3b(a, x, g); }
+const double* oracle_mbnrg_coef_3b(int ion) { return ORC_NRG_COEF_3B + 1831 * (ion - 1); }
+int oracle_mbnrg_have_reference_3b() { return ref_handle != nullptr && ref_3b[0] != nullptr; }
+
+// one ion-water-water cluster; the gradients are zeroed first, as do_trimer does (mbnrg.f90:864-866)
+void oracle_mbnrg_h2o_h2o_ion(int use_ref, int ion, const double* w1, const double* w2, const double* x, double* E, double* g1, double* g2,
+                              double* g3)
+{
+    std::fill(g1, g1 + 9, 0.0);
+    std::fill(g2, g2 + 9, 0.0);
+    std::fill(g3, g3 + 3, 0.0);
+    if (use_ref && ref_3b[ion - 1]) ref_3b[ion - 1](w1, w2, x, E, g1, g2, g3);
+    else *E = eval_h2o_h2o_ion(ion, w1, w2, x, g1, g2, g3);
+}
+
+// The 3B part of mbnrg_forces (mbnrg.f90:354-427, do_trimer :781-993; disabled in the reference build by `!#define ENABLE_X3B`, :4):
+// for every ion k and every water pair i < j, with the minimum-image vectors O_i - O_j, O_j - X, O_i - X: the trimer is evaluated iff
+// |O_i - X| < r3f AND |O_j - X| < r3f (r3f = 7, :135; strict <, :840-842); water i and the ion are placed next to water j (:849-858);
+// energy, virial, stress (computed 1,2,3,5,6,9; mirrored 4,7,8) and forces accumulate as in do_trimer.  Canonical semantics:
+// the stored monomers are not mutated.  Rank r of nranks takes the contiguous range [T r/N, T (r+1)/N) of the accepted trimers in
+// (k, i, j) order.  counts[0] = accepted trimers (all ranks), counts[1] = evaluated by this rank.
+int oracle_mbnrg_forces3(int use_ref, int rank, int nranks, int imcon, const double* cell, int nttm2, const int* listttm2, int nions,
+                         const int* listions, const int* ion_code, const double* xxx, const double* yyy, const double* zzz, double* fxx,
+                         double* fyy, double* fzz, double* eng3, double* vir3, double* stress, long long* counts)
+{
+    const double r3f = 7.0;
+    const int nw = nttm2 / 3;
+    std::vector<double> wat(9 * (size_t)nw), ion(3 * (size_t)nions);
+    for (int t = 0; t < nttm2; ++t) {
+        const int i = listttm2[t] - 1;
+        wat[3 * t + 0] = xxx[i]; wat[3 * t + 1] = yyy[i]; wat[3 * t + 2] = zzz[i];
+    }
+    for (int t = 0; t < nions; ++t) { ion[3 * t + 0] = xxx[t]; ion[3 * t + 1] = yyy[t]; ion[3 * t + 2] = zzz[t]; }
+    oracle_image_monomers(imcon, cell, nw, wat.data());
+    struct Tri { int k, i, j; };
+    std::vector<Tri> tris;
+    for (int k = 0; k < nions; ++k) {
+        std::vector<int> near;
+        for (int i = 0; i < nw; ++i) {
+            double r[3] = {wat[9 * i] - ion[3 * k], wat[9 * i + 1] - ion[3 * k + 1], wat[9 * i + 2] - ion[3 * k + 2]};
+            if (oracle_image_vectors(imcon, cell, 1, r)) return 1;
+            if (std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) < r3f) near.push_back(i);
+        }
+        for (size_t p = 0; p < near.size(); ++p)
+            for (size_t q = p + 1; q < near.size(); ++q) tris.push_back({k, near[p], near[q]});
+    }
+    const long long T = (long long)tris.size(), lo = T * rank / nranks, hi = T * (rank + 1) / nranks;
+    double e3 = 0.0, v3 = 0.0;
+    for (long long t = lo; t < hi; ++t) {
+        const Tri& tr = tris[t];
+        const double* wi = &wat[9 * (size_t)tr.i];
+        const double* w2 = &wat[9 * (size_t)tr.j];
+        const double* xk = &ion[3 * (size_t)tr.k];
+        double rab[6] = {wi[0] - w2[0], wi[1] - w2[1], wi[2] - w2[2], w2[0] - xk[0], w2[1] - xk[1], w2[2] - xk[2]};
+        if (oracle_image_vectors(imcon, cell, 2, rab)) return 1;
+        double w1[9], x[3];
+        for (int q = 0; q < 3; ++q) {
+            w1[3 + q] = (wi[3 + q] - wi[q]) + (w2[q] + rab[q]);
+            w1[6 + q] = (wi[6 + q] - wi[q]) + (w2[q] + rab[q]);
+            w1[q] = w2[q] + rab[q];
+            x[q] = w2[q] - rab[3 + q];
+        }
+        double E, g1[9], g2[9], g3[3];
+        oracle_mbnrg_h2o_h2o_ion(use_ref, ion_code[tr.k], w1, w2, x, &E, g1, g2, g3);
+        e3 += E * engunit;
+        for (int q = 0; q < 9; ++q) { g1[q] *= engunit; g2[q] *= engunit; v3 += w1[q] * g1[q] + w2[q] * g2[q]; }
+        for (int q = 0; q < 3; ++q) { g3[q] *= engunit; v3 += x[q] * g3[q]; }
+        const int o1 = listttm2[3 * tr.i], o2 = listttm2[3 * tr.j], o3 = listions[tr.k];
+        for (int q = 0; q < 3; ++q) {
+            fxx[o1 - 1 + q] -= g1[3 * q]; fyy[o1 - 1 + q] -= g1[3 * q + 1]; fzz[o1 - 1 + q] -= g1[3 * q + 2];
+            fxx[o2 - 1 + q] -= g2[3 * q]; fyy[o2 - 1 + q] -= g2[3 * q + 1]; fzz[o2 - 1 + q] -= g2[3 * q + 2];
+        }
+        fxx[o3 - 1] -= g3[0]; fyy[o3 - 1] -= g3[1]; fzz[o3 - 1] -= g3[2];
+        for (int a = 0; a < 3; ++a)
+            for (int b = a; b < 3; ++b) {
+                double sacc = x[a] * g3[b];
+                for (int q = 0; q < 3; ++q) sacc += w1[3 * q + a] * g1[3 * q + b] + w2[3 * q + a] * g2[3 * q + b];
+                stress[3 * a + b] -= sacc;
+                if (b > a) stress[3 * b + a] -= sacc;
+            }
+    }
+    *eng3 += e3;
+    *vir3 += v3;
+    if (counts) { counts[0] = T; counts[1] = hi - lo; }
     return 0;
 }
 

@@ -85,6 +85,43 @@ class Oracle:
         have = self.lib.oracle_mbnrg_ion_ion(int(ref), int(a), int(b), _p(w), _p(x), C.byref(E), _p(g1), _p(g2))
         return bool(have), E.value, g1, g2
 
+    def nrg_poly3b(self, a, x):
+        a, x, g = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(x, dtype=np.float64), np.zeros(21)
+        self.lib.oracle_mbnrg_poly3b.restype = C.c_double
+        return self.lib.oracle_mbnrg_poly3b(_p(a), _p(x), _p(g)), g
+
+    def nrg_coef_3b(self, ion):
+        self.lib.oracle_mbnrg_coef_3b.restype = _dp
+        return np.ctypeslib.as_array(self.lib.oracle_mbnrg_coef_3b(int(ion)), shape=(1831,)).copy()
+
+    @property
+    def have_nrg_reference_3b(self):
+        return bool(self.have_nrg_reference and self.lib.oracle_mbnrg_have_reference_3b())
+
+    def nrg_h2o_h2o_ion(self, ion, w1, w2, x, ref=False):
+        """mbnrg_3b_h2o_h2o_<ion>_poly_ (restatement, or the reference object with ref=True)."""
+        w1, w2, x = (np.ascontiguousarray(v, dtype=np.float64) for v in (w1, w2, x))
+        E, g1, g2, g3 = C.c_double(), np.zeros(9), np.zeros(9), np.zeros(3)
+        self.lib.oracle_mbnrg_h2o_h2o_ion(int(ref), int(ion), _p(w1), _p(w2), _p(x), C.byref(E), _p(g1), _p(g2), _p(g3))
+        return E.value, g1, g2, g3
+
+    def nrg_forces3(self, box, use_ref=False, rank=0, nranks=1):
+        """The 3B ion-water-water part of mbnrg_forces (disabled in the reference build, mbnrg.f90:4) on a synth.make_ion_box dict."""
+        n = box["mxatms"]
+        f = [np.zeros(n) for _ in range(3)]
+        e, v, st, cnt = C.c_double(0.0), C.c_double(0.0), np.zeros(9), np.zeros(2, dtype=np.int64)
+        lt = np.ascontiguousarray(box["listttm2"], dtype=np.int32)
+        li = np.ascontiguousarray(box["listions"], dtype=np.int32)
+        ic = np.ascontiguousarray(box["ion_code"], dtype=np.int32)
+        cell = np.ascontiguousarray(box["cell"], dtype=np.float64)
+        rc = self.lib.oracle_mbnrg_forces3(int(use_ref), int(rank), int(nranks), int(box["imcon"]), _p(cell), int(box["nttm2"]),
+                                           lt.ctypes.data_as(_ip), int(box["nions"]), li.ctypes.data_as(_ip), ic.ctypes.data_as(_ip),
+                                           _p(box["xxx"]), _p(box["yyy"]), _p(box["zzz"]), _p(f[0]), _p(f[1]), _p(f[2]),
+                                           C.byref(e), C.byref(v), _p(st), cnt.ctypes.data_as(C.POINTER(C.c_longlong)))
+        if rc:
+            raise RuntimeError("oracle_mbnrg_forces3 failed (%d)" % rc)
+        return dict(eng3=e.value, vir3=v.value, stress=st, fxx=f[0], fyy=f[1], fzz=f[2], ntrimers=int(cnt[0]), nshard=int(cnt[1]))
+
     def nrg_forces(self, box, use_ref=False, rank=0, nranks=1):
         """mbnrg_forces on a box dict of synth.make_ion_box: returns eng2, vir2, stress, forces and the pair counts."""
         n = box["mxatms"]

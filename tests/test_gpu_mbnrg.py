@@ -167,3 +167,64 @@ def test_degenerate_sizes():
                            np.zeros(3), f[0], f[1], f[2], st)
     assert r["eng2"] == 0.0 and not np.any(f[0])
     mbnrg.mbnrg_fini(h)
+
+
+# ---- 3B ion-water-water ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gold3():
+    return np.load(os.path.join(ROOT, "tests", "golden", "mbnrg3.npz"))
+
+
+def test_3b_golden_vectors(handle, gold3):
+    """mbnrg_b200_eval_h2o_h2o_ion against the reference objects' outputs for all nine ion species (2e-10 of max(|E|,|g|): the
+    fitted coefficients cancel heavily, see tests/test_mbnrg.py)."""
+    for ion in range(1, 10):
+        sel = gold3["tri_ion"] == ion
+        E, g = mbnrg.mbnrg_eval_h2o_h2o_ion(handle, ion, gold3["tri_w"][sel])
+        sc = np.maximum(np.abs(gold3["tri_E"][sel]), np.abs(gold3["tri_g"][sel]).max(1))
+        assert np.all(np.abs(E - gold3["tri_E"][sel]) <= 2e-10 * sc), ion
+        assert np.all(np.abs(g - gold3["tri_g"][sel]).max(1) <= 2e-10 * sc), ion
+
+
+def _check_3b(out, ref, cnt):
+    assert cnt["ntrimers"] == ref["ntrimers"]
+    assert abs(out["eng3"] - ref["eng3"]) <= 1e-10 * abs(ref["eng3"])
+    assert abs(out["vir3"] - ref["vir3"]) <= 1e-9 * abs(ref["vir3"])
+    for k in ("fxx", "fyy", "fzz"):
+        assert rel_rms(out[k], ref[k]) <= 1e-9, k
+    assert np.abs(out["stress"] - ref["stress"]).max() <= 1e-9 * np.abs(ref["stress"]).max()
+
+
+def test_3b_small_box_against_golden(oracle, synth, gold3):
+    box = synth.make_ion_box(216, 8)
+    h = mbnrg.mbnrg_init(box["nttm2"], box["ion_code"])
+    out = mbnrg.run_ion_box_3b(h, box)
+    cnt = mbnrg.mbnrg_counts_3b(h)
+    mbnrg.mbnrg_fini(h)
+    ref = dict(eng3=gold3["box_scalars"][0], vir3=gold3["box_scalars"][1], stress=gold3["box_stress"], fxx=gold3["box_fxx"],
+               fyy=gold3["box_fyy"], fzz=gold3["box_fzz"], ntrimers=int(gold3["box_counts"][0]))
+    _check_3b(out, ref, cnt)
+
+
+def test_3b_nacl_box_config4(oracle, synth):
+    """BASELINE config 4 with the 3B term: 4032 H2O + 64 Na/Cl, ~70 k ion-water-water trimers against the oracle driver around the
+    reference's evaluator objects; three shards add up to the whole."""
+    box = synth.make_ion_box(4096, 64)
+    h = mbnrg.mbnrg_init(box["nttm2"], box["ion_code"])
+    out = mbnrg.run_ion_box_3b(h, box)
+    cnt = mbnrg.mbnrg_counts_3b(h)
+    ref = oracle.nrg_forces3(box, use_ref=oracle.have_nrg_reference_3b)
+    assert ref["ntrimers"] > 30000
+    _check_3b(out, ref, cnt)
+    assert abs(sum(out[k].sum() for k in ("fxx", "fyy", "fzz"))) <= 1e-7 * np.abs(out["fxx"]).max()
+    tot = {k: np.zeros_like(out[k]) for k in ("fxx", "fyy", "fzz", "stress")}
+    e, n = 0.0, 0
+    for rank in range(3):
+        mbnrg.mbnrg_set_shard(h, rank, 3)
+        o = mbnrg.run_ion_box_3b(h, box)
+        n += mbnrg.mbnrg_counts_3b(h)["nshard"]
+        e += o["eng3"]
+        for k in tot:
+            tot[k] += o[k]
+    mbnrg.mbnrg_fini(h)
+    assert n == ref["ntrimers"] and abs(e - out["eng3"]) <= 1e-11 * abs(e) and rel_rms(tot["fxx"], out["fxx"]) <= 1e-11

@@ -130,7 +130,7 @@ def test_generated_schedule_matches_table(tmp_path, oracle):
 def test_abi_symbols_and_loud_failure():
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mbnrg_b200.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(mbnrg_b200_\w+)\s*\(", txt)))
-    assert len(names) == 9 and "mbnrg_b200_forces" in names
+    assert len(names) == 12 and "mbnrg_b200_forces" in names and "mbnrg_b200_forces_3b" in names
     lib = mb.load_library()
     for n in names:
         assert hasattr(lib, n), "symbol %s declared in include/mbnrg_b200.h but not exported" % n
@@ -152,3 +152,69 @@ def test_ion_box_generator(synth):
     assert box["ion_code"].tolist() == [6, 2] * 4
     b2 = synth.make_ion_box(216, 8)
     assert np.array_equal(box["xxx"], b2["xxx"])
+
+
+# ---- 3B ion-water-water (mbnrg-3b-h2o-h2o-<ion>-poly.cpp; compiled out in the reference build, mbnrg.f90:4) -------------------
+@pytest.fixture(scope="module")
+def gold3():
+    return np.load(os.path.join(ROOT, "tests", "golden", "mbnrg3.npz"))
+
+
+def test_oracle_3b_matches_reference_vectors(oracle, gold3):
+    """The restated x3b_h2o_ion_v2x_p::operator() (21 variables, table-driven 1831-coefficient polynomial) against the golden vectors the
+    reference's own objects produced for all nine ion species.  The fitted coefficients cancel heavily (|a| up to 1e3 for |E| ~ 1),
+    so two summation orders agree to ~1e-11 of max(|E|, |g|) per cluster, not better."""
+    for q in range(len(gold3["tri_ion"])):
+        w = gold3["tri_w"][q]
+        E, g1, g2, g3 = oracle.nrg_h2o_h2o_ion(int(gold3["tri_ion"][q]), w[:9], w[9:18], w[18:])
+        sc = max(abs(gold3["tri_E"][q]), np.abs(gold3["tri_g"][q]).max())
+        assert abs(E - gold3["tri_E"][q]) <= 2e-10 * sc, q
+        assert np.abs(np.r_[g1, g2, g3] - gold3["tri_g"][q]).max() <= 2e-10 * sc, q
+        assert np.abs(np.r_[g1, g2, g3].reshape(7, 3).sum(0)).max() <= 1e-9 * sc          # no net force on the cluster
+
+
+def test_oracle_3b_box_matches_reference_driver(oracle, gold3, synth):
+    """The restated 3B driver (both oxygen-ion distances < 7 A, water i and ion placed next to water j) on the 208-water + 8-ion box."""
+    box = synth.make_ion_box(216, 8)
+    r = oracle.nrg_forces3(box, use_ref=oracle.have_nrg_reference_3b)
+    assert r["ntrimers"] == int(gold3["box_counts"][0]) and r["ntrimers"] > 1000
+    assert abs(r["eng3"] - gold3["box_scalars"][0]) <= 1e-10 * abs(gold3["box_scalars"][0])
+    assert abs(r["vir3"] - gold3["box_scalars"][1]) <= 1e-9 * abs(gold3["box_scalars"][1])
+    for k in ("fxx", "fyy", "fzz"):
+        assert np.sqrt(np.mean((r[k] - gold3["box_" + k]) ** 2) / np.mean(gold3["box_" + k] ** 2)) <= 1e-9
+    assert np.abs(r["stress"] - gold3["box_stress"]).max() <= 1e-9 * np.abs(gold3["box_stress"]).max()
+    # two ranks partition the trimer list and add up
+    a, b = oracle.nrg_forces3(box, use_ref=oracle.have_nrg_reference_3b, rank=0, nranks=2), oracle.nrg_forces3(box, use_ref=oracle.have_nrg_reference_3b, rank=1, nranks=2)
+    assert a["nshard"] + b["nshard"] == r["ntrimers"]
+    assert abs(a["eng3"] + b["eng3"] - r["eng3"]) <= 1e-11 * abs(r["eng3"])
+
+
+def test_generated_3b_schedule_matches_table(oracle):
+    """tools/gen_mbnrg.py: the 24-part shared-prefix Horner schedule of the 3B polynomial (what the GPU runs), executed here in Python on
+    the per-thread record, equals the raw monomial table."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_mbnrg
+    import gen_poly
+    d = np.load(gen_mbnrg.DATA)
+    sch = gen_poly.make_schedule(d["mono_3b"], 21, "greedy")
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0.2, 1.1, size=21)
+    a = oracle.nrg_coef_3b(6)
+    reg = {}
+    val = lambda o: a[o[1]] if o[0] == "c" else (x[o[1]] if o[0] == "x" else reg[o])
+    for op in sch.ops:
+        if op[0] == "fma":
+            reg[op[1]] = val(op[2]) * val(op[3]) + val(op[4])
+        elif op[0] == "mul":
+            reg[op[1]] = val(op[2]) * val(op[3])
+        elif op[0] == "add":
+            reg[op[1]] = val(op[2]) + val(op[3])
+        elif op[0] == "mov":
+            reg[op[1]] = val(op[2])
+    E, g = oracle.nrg_poly3b(a, x)
+    gs = np.array([reg[("g", i)] for i in range(21)])
+    sc = max(abs(E), np.abs(g).max())
+    assert abs(reg[("E",)] - E) <= 1e-9 * sc and np.abs(gs - g).max() <= 1e-9 * sc
+    # every part of the split loads only what an earlier part stored
+    parts = gen_poly.split_parts(sch.ops, gen_mbnrg.NPART3, 21)
+    assert len(parts) == gen_mbnrg.NPART3 and not parts[0][1]

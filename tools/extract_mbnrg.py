@@ -13,6 +13,9 @@ Output: dlpoly2-mbpol-heat_b200/data/mbnrg_model.npz
                                      d_XO_coul d_XLp_main in_plane_gamma out_of_plane_gamma r2i r2f
     mono_ii   int16 [13, 14] / w_ii  the 1-variable ion-ion polynomial  sum_n a[n-1] x^n
     coef_ii   float64 [9, 9, 13], par_ii float64 [9, 9, 4] (k_AB d_AB r2i r2f), have_ii bool [9, 9] (symmetric)
+    mono_3b   int16 [n, 6] / w_3b    the 21-variable, degree-5 ion-water-water polynomial (poly-3b-h2o-ion-v1x.cpp)
+    coef_3b   float64 [9, 1831]      mbnrg-3b-h2o-h2o-<ion>-poly.cpp
+    par_3b    float64 [9, 16]        r3i r3f kHH_intra kOH_intra kHH kOH kOO kXH kXO dHH_intra dOH_intra dHH dOH dOO dXH dXO
 """
 import os
 import re
@@ -25,6 +28,10 @@ import extract_model as X
 IONS = ["f", "cl", "br", "i", "li", "na", "k", "rb", "cs"]
 PAR_HI = ["m_k_HH_intra", "m_k_OH_intra", "m_k_XH_coul", "m_k_XO_coul", "m_k_XLp_main", "m_d_HH_intra", "m_d_OH_intra",
           "m_d_XH_coul", "m_d_XO_coul", "m_d_XLp_main", "m_in_plane_gamma", "m_out_of_plane_gamma", "m_r2i", "m_r2f"]
+
+
+PAR_3B = ["m_r3i", "m_r3f", "m_kHH_intra", "m_kOH_intra", "m_kHH", "m_kOH", "m_kOO", "m_kXH", "m_kXO", "m_dHH_intra", "m_dOH_intra", "m_dHH",
+          "m_dOH", "m_dOO", "m_dXH", "m_dXO"]
 
 
 def table(p, ncoef, maxdeg):
@@ -77,6 +84,19 @@ def main():
             for (u, v) in ((i, j), (j, i)):
                 cii[u, v], pii[u, v], have[u, v] = c, [pp[n] for n in names + ["m_r2i", "m_r2f"]], True
     out["coef_ii"], out["par_ii"], out["have_ii"] = cii, pii, have
+    # ---- 3B ion-water-water (mbnrg-3b-h2o-h2o-<ion>-poly.cpp, poly-3b-h2o-ion-v1x.cpp: 21 variables, 1831 coefficients, degree 5)
+    p, nused, ntot = X.symbolic_energy(os.path.join(ref, "poly-3b-h2o-ion-v1x.cpp"))
+    out["mono_3b"], out["w_3b"] = table(p, 1831, 5)
+    assert np.all(out["w_3b"] == 1.0)
+    deg = (out["mono_3b"][:, 1:] >= 0).sum(1)
+    print("h2o-h2o-ion: %d/%d statements feed E; %d monomials (deg hist %s)" % (nused, ntot, len(out["mono_3b"]), np.bincount(deg).tolist()))
+    c3, p3 = np.zeros((9, 1831)), np.zeros((9, 16))
+    for i, ion in enumerate(IONS):
+        src = open(os.path.join(ref, "mbnrg-3b-h2o-h2o-%s-poly.cpp" % ion)).read()
+        c3[i] = X.literal_block(src, "the_poly[] = {")
+        pp = X.named_params(src, PAR_3B)
+        p3[i] = [pp[k] for k in PAR_3B]
+    out["coef_3b"], out["par_3b"] = c3, p3
     print("ion-ion pairs with a fitted evaluator: %d of 45" % (np.triu(have).sum()))
     dst = os.path.join(X.DATA, "mbnrg_model.npz")
     np.savez_compressed(dst, **out)
