@@ -212,13 +212,15 @@ def run_ions(args, mb, synth):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             r = o.nrg_forces(box, use_ref=o.have_nrg_reference)
+            r3 = o.nrg_forces3(box, use_ref=o.have_nrg_reference_3b)      # the 3B term BASELINE config 4 names (off in the reference build)
         dt = (time.perf_counter() - t0) / args.steps
         v = r["nactive"] / dt
         print(json.dumps({"impl": "reference", "metric": "mbnrg_ion_water_pairs_per_second", "value": v, "unit": "pairs/s", "n_gpus": 1,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "NaCl(aq) MB-nrg 2B: %d H2O + %d Na/Cl" % (box["nw"], box["nions"]),
-                                     "pairs_within_10A": r["npairs"], "pairs_evaluated": r["nactive"], "ion_ion_pairs": r["nionion"]},
+                          "config": {"workload": "NaCl(aq) MB-nrg 2B + 3B: %d H2O + %d Na/Cl" % (box["nw"], box["nions"]),
+                                     "pairs_within_10A": r["npairs"], "pairs_evaluated": r["nactive"], "ion_ion_pairs": r["nionion"],
+                                     "trimers_3b": r3["ntrimers"]},
                           "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": 1, "kind": "reference" if o.have_nrg_reference else "port",
                                            "sample": "the whole step"},
                           "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -227,8 +229,11 @@ def run_ions(args, mb, synth):
     n = box["mxatms"]
     F = [np.zeros(n) for _ in range(3)]
     st = np.zeros(9)
-    call = lambda: mbnrg.mbnrg_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"],
-                                      box["xxx"], box["yyy"], box["zzz"], F[0], F[1], F[2], st)
+    def call():      # the 2B call and the optional 3B call, as mbnrg_forces does with ENABLE_X2B and ENABLE_X3B (mbnrg.f90:255-427)
+        mbnrg.mbnrg_forces(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"],
+                           box["xxx"], box["yyy"], box["zzz"], F[0], F[1], F[2], st)
+        mbnrg.mbnrg_forces_3b(h, box["imcon"], box["cell"], box["nttm2"], box["listttm2"], box["nions"], box["listions"],
+                              box["xxx"], box["yyy"], box["zzz"], F[0], F[1], F[2], st)
     for _ in range(max(args.warmup, 3)):
         call()
     t, dev = [], []
@@ -236,26 +241,31 @@ def run_ions(args, mb, synth):
         t0 = time.perf_counter()
         call()
         t.append(time.perf_counter() - t0)
-        dev.append(mbnrg.mbnrg_kernel_times(h))
+        dev.append(dict(mbnrg.mbnrg_kernel_times(h), **{"k3b_" + k: v for k, v in mbnrg.mbnrg_counts_3b(h).items() if k.endswith("_ms")}))
     c = mbnrg.mbnrg_counts(h)
-    ms_dev = float(np.mean([d["total_ms"] for d in dev]))
+    c3 = mbnrg.mbnrg_counts_3b(h)
+    ms_dev = float(np.mean([d["total_ms"] + d["k3b_total_ms"] for d in dev]))
     ms_k = float(np.mean([d["h2o_ion_ms"] for d in dev]))
     flop_pair = 3888                                     # multiplies + adds of the reference polynomial body per evaluated pair
+    ms_3b = float(np.mean([d["k3b_eval_ms"] for d in dev]))
     line = {"metric": "mbnrg_ion_water_pairs_per_second", "value": c["nactive"] / (ms_dev * 1e-3), "unit": "pairs/s", "n_gpus": 1,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "NaCl(aq) MB-nrg 2B: %d H2O + %d Na/Cl, ion-water + ion-ion polynomials (3B compiled out in the reference)"
-                       % (box["nw"], box["nions"]), "pairs_within_10A": c["npairs"], "pairs_evaluated": c["nactive"], "ion_ion_pairs": c["nionion"],
+            "config": {"workload": "NaCl(aq) MB-nrg 2B + 3B: %d H2O + %d Na/Cl, ion-water + ion-ion + ion-water-water polynomials (the 3B term is "
+                                   "compiled out in the reference build, mbnrg.f90:4)" % (box["nw"], box["nions"]),
+                       "pairs_within_10A": c["npairs"], "pairs_evaluated": c["nactive"], "ion_ion_pairs": c["nionion"], "trimers_3b": c3["ntrimers"],
                        "l2": "inputs re-uploaded every step"},
             "e2e": {"value": c["nactive"] / float(np.mean(t)), "unit": "pairs/s", "ms_per_step": 1e3 * float(np.mean(t)),
                     "h2d_bytes_per_step": 8 * 3 * n + 4 * (box["nttm2"] + box["nions"]), "d2h_bytes_per_step": 8 * (3 * n + 16)},
-            "gpu_launches": int(dev[-1]["launches"]) * args.steps,
-            "phases_ms": {k: float(np.mean([q[k] for q in dev])) for k in ("pairs_ms", "h2o_ion_ms", "ion_ion_ms", "total_ms")},
+            "gpu_launches": (int(dev[-1]["launches"]) + 4) * args.steps,
+            "phases_ms": {k: float(np.mean([q[k] for q in dev])) for k in ("pairs_ms", "h2o_ion_ms", "ion_ion_ms", "total_ms", "k3b_list_ms", "k3b_eval_ms", "k3b_total_ms")},
             "roofline": {"bound": "latency", "achieved": c["nactive"] * flop_pair / (ms_k * 1e-3) / 1e12, "peak": None, "unit": "TFLOP/s",
                          "frac": None, "traffic": None,
                          "note": "%d pairs x 3888 flops = %.1f MFLOP per launch: %d CTAs of 128 threads cannot fill 148 SMs; the kernel time is "
-                                 "launch + one dependent pass through a 2.4k-instruction body" % (c["nactive"], c["nactive"] * flop_pair / 1e6,
-                                                                                                   (c["nactive"] + 127) // 128)}}
+                                 "launch + one dependent pass through a 2.4k-instruction body.  3B: %d trimers x 25538 FP64 instructions of our "
+                                 "schedule in %.3f ms = %.2f TFLOP/s (2 flop per instruction)" % (
+                                     c["nactive"], c["nactive"] * flop_pair / 1e6, (c["nactive"] + 127) // 128, c3["ntrimers"], ms_3b,
+                                     2 * 25538 * c3["ntrimers"] / (ms_3b * 1e-3) / 1e12)}}
     if not args.no_cpu_baseline:
         from oracle.oracle import Oracle
         o = Oracle()
@@ -263,6 +273,7 @@ def run_ions(args, mb, synth):
         reps = 0
         while time.perf_counter() - t0 < 5.0:
             r = o.nrg_forces(box, use_ref=o.have_nrg_reference)
+            o.nrg_forces3(box, use_ref=o.have_nrg_reference_3b)
             reps += 1
         dt = (time.perf_counter() - t0) / reps
         line["cpu_baseline"] = {"value": r["nactive"] / dt, "unit": "pairs/s", "cores": 1, "kind": "reference" if o.have_nrg_reference else "port",

@@ -79,3 +79,69 @@ def write_config(path, box, forces=None, title="mbpol_b200 water box", nstep=0, 
             out.write(e3(box["xxx"][i], box["yyy"][i], box["zzz"][i]) + "\n")
             out.write(e3(box["vxx"][i], box["vyy"][i], box["vzz"][i]) + "\n")
             out.write(e3(f[0][i], f[1][i], f[2][i]) + "\n")
+
+
+def read_field(path):
+    """Minimal DL_POLY 2 FIELD reader: what the MB-pol path needs from it is the molecular make-up -- molecule types with `nummols` copies
+    of `numsit` sites each (sysdef.f) -- from which ttm2list.f:27-70 derives listttm2: the water is the SECOND TO LAST molecule type (3 sites),
+    the last type holds the M sites (1 site, as many as waters), atoms are numbered type by type, molecule by molecule, site by site, and the
+    heaviest of the three water sites (the oxygen) is moved to the first place of every triple.
+    Returns {"types": [(name, nummols, [(site name, mass, charge), ...])], "natoms", "nttm2", "listttm2" (1-based), "names"}."""
+    with open(path) as f:
+        lines = [ln.rstrip("\n") for ln in f]
+    types, i, ntp = [], 0, None
+    while i < len(lines):
+        key = lines[i].strip().lower()
+        if key.startswith("molecul") and ntp is None:          # "MOLECULES n" / "molecular types n"
+            ntp = int(key.split()[-1])
+            i += 1
+            for _ in range(ntp):
+                name = lines[i].strip()
+                i += 1
+                nummols, sites = 1, []
+                while not lines[i].strip().lower().startswith("finish"):
+                    w = lines[i].split()
+                    k = w[0].lower()
+                    if k.startswith("nummol"):
+                        nummols = int(w[1])
+                        i += 1
+                    elif k.startswith("atoms"):
+                        na = int(w[1])
+                        i += 1
+                        while len(sites) < na:
+                            a = lines[i].split()
+                            rep = int(a[3]) if len(a) > 3 and a[3].lstrip("-").isdigit() else 1
+                            sites += [(a[0], float(a[1]), float(a[2]))] * max(rep, 1)
+                            i += 1
+                    else:                                     # bonds, angles, constraints, rigid units ...: "<keyword> n" + n lines
+                        n = int(w[1]) if len(w) > 1 and w[1].isdigit() else 0
+                        i += 1 + n
+                i += 1
+                types.append((name, nummols, sites))
+        else:
+            i += 1
+    if ntp is None:
+        raise ValueError("no MOLECULES directive in %s" % path)
+    names = [s[0] for (_, nm, sites) in types for _ in range(nm) for s in sites]
+    out = {"types": types, "natoms": len(names), "names": names, "nttm2": 0, "listttm2": np.zeros(0, dtype=np.int32)}
+    if len(types) >= 2 and len(types[-2][2]) == 3 and len(types[-1][2]) == 1 and types[-2][1] == types[-1][1]:      # ttm2list.f:19-30
+        first = sum(nm * len(s) for (_, nm, s) in types[:-2])
+        nw = types[-2][1]
+        lst = np.arange(first + 1, first + 3 * nw + 1, dtype=np.int32).reshape(nw, 3)
+        ox = int(np.argmax([s[1] for s in types[-2][2]]))                                                       # ttm2list.f:54-61
+        if ox != 0:
+            lst[:, [0, ox]] = lst[:, [ox, 0]]
+        out["nttm2"], out["listttm2"] = 3 * nw, lst.ravel().copy()
+    return out
+
+
+def write_field(path, box, title="mbpol_b200 water box"):
+    """FIELD of a synth box: [ions] + `nw` TTM/MB-pol waters (O, H, H) + `nw` M sites, the layout ttm2list.f expects."""
+    nw = int(box["nw"])
+    nions = int(box.get("nions", 0))
+    with open(path, "w") as out:
+        out.write("%s\nUNITS kcal\nMOLECULES %d\n" % (title, 2 + (1 if nions else 0)))
+        if nions:
+            out.write("ions\nNUMMOLS %d\nATOMS 1\nNa+ 22.9898 1.0\nFINISH\n" % nions)
+        out.write("water\nNUMMOLS %d\nATOMS 3\nOW 15.9994 0.0\nHW 1.008 0.0\nHW 1.008 0.0\nFINISH\n" % nw)
+        out.write("msite\nNUMMOLS %d\nATOMS 1\nMW 0.0 0.0\nFINISH\nVDW 0\nCLOSE\n" % nw)

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing without a profiler attached
 #include <nccl.h>      // types and prototypes only: the library is bound at run time (nccl_api below)
 
 #include <algorithm>
@@ -545,7 +546,8 @@ struct mbpol_b200_handle {
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll, counts;
     DevBuf<char> scan_tmp;
-    std::vector<int> host_list;
+    std::vector<int> host_list, list_cache;     // list_cache: the caller's listttm2 of the last upload
+    int list_mxb = -1;
     double* pinned = nullptr;
     size_t pinned_cap = 0;
     std::vector<cudaEvent_t> dl_ev;            // one event behind every piece of the pipelined download
@@ -632,6 +634,12 @@ const NcclApi& nccl_api()
     });
     return api;
 }
+
+// NVTX ranges of the step (the user-visible trace of the reference's three -DDEBUG timers, mbpol.f90:209-212, 280-284, 383-387)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define NCCL_TRY(h, call)                                                                                   \
     do {                                                                                                    \
@@ -771,11 +779,16 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
         h->err = "mbpol_b200_upload: invalid argument (imcon must be 1, 2 or 3; nttm2 must match init)";
         return MBPOL_B200_EINVAL;
     }
-    for (int t = 0; t < nttm2; t += 3)      // H atoms are addressed as o+1, o+2 (mbpol.f90:526-527, 592-594): the whole water must be in range
-        if (listttm2[t] < 1 || listttm2[t] + 2 > mxatms || listttm2[t + 1] < 1 || listttm2[t + 1] > mxatms || listttm2[t + 2] < 1 || listttm2[t + 2] > mxatms) {
-            h->err = "mbpol_b200_upload: listttm2 entry out of range [1, mxatms]";
-            return MBPOL_B200_EINVAL;
-        }
+    // the topology rarely changes between MD steps: it is validated and uploaded only when it differs from the cached copy
+    const bool same_list = h->list_mxb == mxatms && h->list_cache.size() == (size_t)nttm2 &&
+                           std::memcmp(h->list_cache.data(), listttm2, (size_t)nttm2 * 4) == 0;
+    if (!same_list) {
+        for (int t = 0; t < nttm2; t += 3)      // H atoms are addressed as o+1, o+2 (mbpol.f90:526-527, 592-594): the whole water must be in range
+            if (listttm2[t] < 1 || listttm2[t] + 2 > mxatms || listttm2[t + 1] < 1 || listttm2[t + 1] > mxatms || listttm2[t + 2] < 1 || listttm2[t + 2] > mxatms) {
+                h->err = "mbpol_b200_upload: listttm2 entry out of range [1, mxatms]";
+                return MBPOL_B200_EINVAL;
+            }
+    }
     CUDA_TRY(h, cudaSetDevice(h->device));
     // bead-batched handles: the arrays hold nbeads consecutive systems of mxatms atoms (one bead otherwise)
     h->mxb = mxatms;
@@ -814,9 +827,16 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p, xxx, n * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + n, yyy, n * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->xyz.p + 2 * n, zzz, n * 8, cudaMemcpyHostToDevice, h->stream));
-    if (h->nbeads == 1) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->list.p, listttm2, (size_t)nttm2 * 4, cudaMemcpyHostToDevice, h->stream));
-    } else {   // the same topology in every bead: atom indices shifted by the bead's offset into the concatenated arrays
+    if (same_list) {
+        // device copy is current
+    } else if (h->nbeads == 1) {
+        h->list_cache.assign(listttm2, listttm2 + nttm2);
+        h->list_mxb = mxatms / h->nbeads;
+        CUDA_TRY(h, cudaMemcpyAsync(h->list.p, h->list_cache.data(), (size_t)nttm2 * 4, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else {
+        h->list_cache.assign(listttm2, listttm2 + nttm2);
+        h->list_mxb = mxatms / h->nbeads;   // the same topology in every bead: atom indices shifted by the bead's offset into the concatenated arrays
         h->host_list.resize((size_t)nttm2 * h->nbeads);
         for (int b = 0; b < h->nbeads; ++b)
             for (int t = 0; t < nttm2; ++t) h->host_list[(size_t)b * nttm2 + t] = listttm2[t] + b * h->mxb;
@@ -884,6 +904,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->unsorted.p);
     k_sort_cells<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->unsorted.p, h->sorted.p);
     h->launches += 6;
+    nvtxRangePushA("mbpol_b200: lists");
     const int gw = (int)(((size_t)std::max(nown, 1) * 32 + TB - 1) / TB);      // one warp per owned water
     if (nown > 0) {
         k_neighbours<<<gw, TB, 0, s>>>(w0, nown, nw, h->mono.p, h->C, h->G, h->cell_cnt.p, h->sorted.p, h->nb2.p, h->n2.p, h->nb3.p, h->n3.p, h->flag.p);
@@ -925,9 +946,11 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     k_publish_counts<<<1, 1, 0, s>>>(h->off2.p + nown, h->off3.p + nown, cap2, cap3, h->est_nd, h->est_nt, h->counts.p, O.scal);
     ++h->launches;
     CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
+    nvtxRangePop();
 
     // ---- 2B ---------------------------------------------------------------------------------------------------------
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
+    nvtxRangePushA("mbpol_b200: 2B");
     if (h->est_nd > 0) {
         const unsigned gd = (unsigned)((h->est_nd + MBPOL_BS2 - 1) / MBPOL_BS2);
         const unsigned gi = (unsigned)std::min<long long>((2 * h->est_nd + 255) / 256, 1 << 20);
@@ -944,6 +967,8 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         h->launches += 6;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
+    nvtxRangePop();
+    nvtxRangePushA("mbpol_b200: 3B");
     // ---- 3B: incidence lists of the shard (count -> exclusive scan -> fill), records, gather -----------------------------
     if (h->est_nt > 0) {
         const unsigned gt = (unsigned)((h->est_nt + MBPOL_BS3 - 1) / MBPOL_BS3);
@@ -968,6 +993,8 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         for (int k = 5; k < 8; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
+    nvtxRangePop();
+    NvtxRange tail_range("mbpol_b200: flux + reduction + read-back");
     if (h->have_vel) {
         k_flux<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
         ++h->launches;
@@ -1022,6 +1049,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
 int mbpol_b200_compute(mbpol_b200_handle* h)
 {
     if (!h || !h->uploaded) return MBPOL_B200_EINVAL;
+    NvtxRange range("mbpol_b200_compute");
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = compute_once(h, h->est_nd >= 0 && h->est_nt >= 0);
     if (rc == -1) {      // rare: the lists outgrew the previous step's counts by > 25 % (collective decision, see k_publish_counts)
@@ -1035,6 +1063,7 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
                         double* vir3, double* stress, double* atomic_energy, double* atomic_stress, double* atomic_fdecomp, double* jflux)
 {
     if (!h || !h->uploaded || !fxx || !fyy || !fzz) return MBPOL_B200_EINVAL;
+    NvtxRange range("mbpol_b200_download");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const size_t n = h->mxatms, cnt = h->out_count();
     if (h->pinned_cap < cnt) {
@@ -1079,7 +1108,7 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
     CUDA_TRY(h, cudaMemcpyAsync(P + so, h->out.p + so, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nth = total < (1u << 18) ? 1u : std::min(8u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
+    const unsigned nth = total < (1u << 20) ? 1u : std::min(8u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
     auto work = [&](unsigned t) {
         cudaSetDevice(h->device);
         for (size_t k = 0; k < jobs.size(); ++k) {

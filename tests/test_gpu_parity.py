@@ -419,3 +419,29 @@ def test_unphysical_density_is_reported_not_truncated(mb):
         mb.run_box(h, box)
     assert "status 3" in str(e.value)
     mb.mbpol_fini(h)
+
+
+def test_config_and_field_files_feed_the_path(mb, synth, tmp_path):
+    """Row f4: a box written as DL_POLY CONFIG + FIELD (centroid_write_config.f:38-87 format, ttm2list.f numbering), read back and
+    evaluated, reproduces the result of the in-memory synthetic box bit for bit (the files carry 17 significant digits)."""
+    from mbpol_b200 import config_io
+    box = synth.make_water_box(256)
+    config_io.write_config(str(tmp_path / "CONFIG"), box)
+    config_io.write_field(str(tmp_path / "FIELD"), box)
+    b2 = config_io.read_config(str(tmp_path / "CONFIG"))
+    fld = config_io.read_field(str(tmp_path / "FIELD"))
+    assert fld["natoms"] == b2["mxatms"] and np.array_equal(fld["listttm2"], b2["listttm2"]) and np.array_equal(fld["listttm2"], box["listttm2"])
+    b2["listttm2"], b2["nttm2"] = fld["listttm2"], fld["nttm2"]                 # the topology comes from FIELD, as in the reference
+    h = mb.mbpol_init(box["nttm2"], flags=7)
+    a = mb.run_box(h, box, want_stress=True)
+    d1, t1 = mb.mbpol_lists(h)
+    b = mb.run_box(h, b2, want_stress=True)
+    d2, t2 = mb.mbpol_lists(h)
+    mb.mbpol_fini(h)
+    assert np.array_equal(sort_rows(d1), sort_rows(d2)) and np.array_equal(sort_rows(t1), sort_rows(t2))
+    for k in ("xxx", "yyy", "zzz", "vxx"):
+        assert np.array_equal(box[k], b2[k]), k                                # the file round trip is exact
+    for k in ("eng2", "eng3", "vir2", "vir3"):
+        assert abs(a[k] - b[k]) <= 1e-12 * abs(a[k]), k                        # (sums run in a different order from call to call)
+    for k in ("fxx", "fyy", "fzz", "atomic_energy", "atomic_stress", "atomic_fdecomp"):
+        assert rel_rms(b[k], a[k]) <= 1e-12, k
