@@ -695,10 +695,14 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     if (ensure_constants(device)) return MBPOL_B200_ECUDA;
     auto* h = new mbpol_b200_handle;
     h->device = device; h->nbeads = nbeads; h->nwb = nttm2 / 3; h->nw = nbeads * h->nwb; h->flags = flags; h->engine = default_engine(); h->engine2b = default_engine_2b();
-    if (allow_smem(k_dimers<1>, SMEM2B) != cudaSuccess || allow_smem(k_dimers<3>, SMEM2B) != cudaSuccess || allow_smem(k_trimers<1>, SMEM3B) != cudaSuccess ||
-        allow_smem(k_trimers<3>, SMEM3B) != cudaSuccess || allow_smem(k_trimers<4>, SMEM3S) != cudaSuccess) {
-        delete h;
-        return MBPOL_B200_ECUDA;
+    {   // dynamic shared memory of the selected engines (a build with more warps per SM may leave no room for the engines it does not use)
+        cudaError_t e2 = h->engine2b == 3 ? allow_smem(k_dimers<3>, SMEM2B) : allow_smem(k_dimers<1>, SMEM2B);
+        cudaError_t e3 = h->engine == 4 ? allow_smem(k_trimers<4>, SMEM3S) : (h->engine == 3 ? allow_smem(k_trimers<3>, SMEM3B) : allow_smem(k_trimers<1>, SMEM3B));
+        if (e2 != cudaSuccess || e3 != cudaSuccess) {
+            cudaGetLastError();
+            delete h;
+            return MBPOL_B200_ECUDA;
+        }
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
@@ -1274,8 +1278,8 @@ static int eval_clusters(int n, int nat3, const double* w, double* E, double* g,
     if (ok(cudaMalloc(&dw, (size_t)n * nat3 * 8)) && ok(cudaMalloc(&dE, (size_t)n * 8)) && ok(cudaMalloc(&dg, (size_t)n * nat3 * 8)) &&
         (!fm || ok(cudaMalloc(&dfm, (size_t)n * fmlen * 8))) && ok(cudaMemcpy(dw, w, (size_t)n * nat3 * 8, cudaMemcpyHostToDevice))) {
         const int eng = default_engine(), eng2 = default_engine_2b();
-        ok(allow_smem(k_eval_dimers<1>, SMEM2B)); ok(allow_smem(k_eval_dimers<3>, SMEM2B));
-        ok(allow_smem(k_eval_trimers<1>, SMEM3B)); ok(allow_smem(k_eval_trimers<3>, SMEM3B)); ok(allow_smem(k_eval_trimers<4>, SMEM3S));
+        if (nat3 == 18) ok(eng2 == 3 ? allow_smem(k_eval_dimers<3>, SMEM2B) : allow_smem(k_eval_dimers<1>, SMEM2B));
+        else ok(eng == 4 ? allow_smem(k_eval_trimers<4>, SMEM3S) : (eng == 3 ? allow_smem(k_eval_trimers<3>, SMEM3B) : allow_smem(k_eval_trimers<1>, SMEM3B)));
         if (nat3 == 18) {
             if (eng2 == 3) k_eval_dimers<3><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_fat2b[device]);
             else k_eval_dimers<1><<<(n + MBPOL_BS2 - 1) / MBPOL_BS2, MBPOL_BS2, SMEM2B>>>(n, dw, dE, dg, dfm, g_tape2b[device]);

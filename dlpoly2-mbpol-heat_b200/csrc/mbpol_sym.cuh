@@ -8,6 +8,8 @@
 // LDS.128, one loop over the super rows of a chunk with the shape dispatch inside.
 #pragma once
 #include "mbpol_tape.cuh"
+// acc += a * b with the operand order fixed in PTX (tools/gen_sym.py --asmfma 1)
+#define SYM_FMA(acc, a, b) asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b))
 #ifndef MBPOL_SYM_HEADER
 #define MBPOL_SYM_HEADER "gen/sym_3b.h"
 #endif

@@ -31,6 +31,7 @@ import gen_poly as G
 
 CHUNK = 2048
 DISPATCH = os.environ.get("SYM_DISPATCH", "if")
+ASMFMA = int(os.environ.get("SYM_ASMFMA", "0"))
 NV = 36
 UNIT = NV
 # atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
@@ -190,7 +191,10 @@ def emit(rows, shapes, vps, ahead, nsum):
                 a = slot(off + 1 + i)
                 for j in range(K):
                     pu = "p2_%d" % j if us[j] == UNIT else "P%d_%d" % (j, k)
-                    body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, %s, g[%d]);" % (acc[j][i % nsum], a, cs[j], acc[j][i % nsum], cs[j], a, pu, cs[j]))
+                    if ASMFMA:      # inline PTX keeps the coefficient in the FIRST multiplicand slot of all 2|K| FMAs (operand reuse cache)
+                        body.append("SYM_FMA(%s, %s, x[%d]); SYM_FMA(g[%d], %s, %s);" % (acc[j][i % nsum], a, cs[j], cs[j], a, pu))
+                    else:
+                        body.append("%s = fma(%s, x[%d], %s); g[%d] = fma(%s, %s, g[%d]);" % (acc[j][i % nsum], a, cs[j], acc[j][i % nsum], cs[j], a, pu, cs[j]))
             nacc = max(1, min(nsum, len(ls)))
             for j in range(K):
                 ssum = " + ".join(acc[j][:nacc])
@@ -248,6 +252,7 @@ def main():
     ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "12")))
     ap.add_argument("--nsum", type=int, default=int(os.environ.get("SYM_NSUM", "1")))
     ap.add_argument("--dispatch", default=DISPATCH, choices=["if", "switch"])
+    ap.add_argument("--asmfma", type=int, default=ASMFMA)
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("SYM_CHUNK", str(CHUNK))), help="doubles per staged tape chunk")
     ap.add_argument("--out", default=os.path.join(G.OUTD, "sym_3b.h"))
     args = ap.parse_args()
@@ -256,6 +261,7 @@ def main():
     ap_dispatch = args.dispatch
     globals()["CHUNK"] = args.chunk
     globals()["DISPATCH"] = ap_dispatch
+    globals()["ASMFMA"] = args.asmfma
     rows, shapes, vps = build(d["mono3b"], args.group, not args.forward, args.repsel)
     txt, nfp, nseg, nch, ntape = emit(rows, shapes, vps, args.ahead, args.nsum)
     open(args.out, "w").write(txt)
