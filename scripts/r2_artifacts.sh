@@ -12,9 +12,9 @@ python bench.py --flags 0 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r
 # launch list of one step (cold-cache, serialised: the SHARES must agree with the bench phases, not the absolute times)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 45 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 2 --no-cpu-baseline > /dev/null 2>&1
 # full captures of the four cluster kernels
-for k in k_trimers\< k_trimers_gather k_dimers\< k_dimers_gather; do
-  tag=r2_$(echo $k | tr -d '<');
-  ncu --set full --clock-control none --import-source on -k regex:"$k" -s 2 -c 1 -f -o gpurun_out/$tag python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/$tag.log 2>&1
+for k in k_trimers k_trimers_gather k_dimers k_dimers_gather; do
+  tag=r2_$k;
+  ncu --set full --clock-control none --import-source on -k regex:"^$k\$" -s 2 -c 1 -f -o gpurun_out/$tag python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/$tag.log 2>&1
   ncu -i gpurun_out/$tag.ncu-rep --page raw --csv > gpurun_out/$tag.raw.csv 2>/dev/null
   ncu -i gpurun_out/$tag.ncu-rep --page source --csv > gpurun_out/$tag.src.csv 2>/dev/null
   python scripts/ncu_summary.py gpurun_out/$tag.raw.csv gpurun_out/$tag.src.csv > gpurun_out/${tag}_ncu.txt 2>&1
