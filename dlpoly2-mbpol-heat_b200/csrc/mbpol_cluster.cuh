@@ -147,8 +147,17 @@ k_trimers(const long long* __restrict__ pcount, const int* __restrict__ tri, int
         const int mi = tri[3 * t], mj = tri[3 * t + 1], mk = tri[3 * t + 2];
         double r[27], xv[36], gp[36], sw[4], Epoly;
         trimer_geometry(nw, mono, C, mi, mj, mk, r);
-        trimer_x_switch(r, xv, sw);
-        poly3b_eval<ENGINE>(xv, gp, Epoly, ctx);
+#ifndef MBPOL_UNROLLED_PROLOGUE
+        if constexpr (ENGINE == 4) {
+            SymSmem& sm = *reinterpret_cast<SymSmem*>(dyn_smem);
+            sym_stage_x(r, sw, sm);
+            sym_eval3b<true>(tape, xv, gp, Epoly, sm);
+        } else
+#endif
+        {
+            trimer_x_switch(r, xv, sw);
+            poly3b_eval<ENGINE>(xv, gp, Epoly, ctx);
+        }
         trimer_record(xv, gp, Epoly, sw, out);
     }
     __syncthreads();      // every thread has read its last gradient column: the column area is free

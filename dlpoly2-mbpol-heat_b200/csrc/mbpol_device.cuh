@@ -151,6 +151,42 @@ __device__ __forceinline__ void trimer_x_switch(const double (&r)[27], double* x
     sw[3] = gbc * (sab + sac);
 }
 
+// The same as a COMPACT LOOP for the box kernel with engine 4 (k_trimers<4>): the 27 coordinates go to the thread's (still
+// idle) gradient columns, a 9 x 4 loop computes distance -> exp and writes x_n straight into the thread's x column, where the
+// tape walk expects it (sym_eval3b<true>).  The unrolled form above is 5 400 instructions that every warp executes once per
+// trimer, i.e. always out of a cold instruction cache (ncu: 35 % of its stall samples are `no_instruction`).
+extern __constant__ unsigned c_v3word[36];      // 3 * V3A[n] | 3 * V3B[n] << 8 | V3K[n] << 16
+__device__ __forceinline__ void sym_stage_x(const double (&r)[27], double (&sw)[4], SymSmem& sm)
+{
+    const unsigned xs_t = (unsigned)__cvta_generic_to_shared(&sm.xs[0][threadIdx.x]);
+    const unsigned rs_t = xs_t + (unsigned)sizeof(sm.xs);          // r[q] in gradient column q, d_OO in columns 27..29
+#pragma unroll
+    for (int q = 0; q < 27; ++q) tape_sts(rs_t + q * TAPE_COL, r[q]);
+#pragma unroll 1
+    for (int n0 = 0; n0 < 36; n0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = n0 + u;
+            const unsigned word = c_v3word[n];
+            const unsigned pa = rs_t + (word & 255u) * TAPE_COL, pb = rs_t + ((word >> 8) & 255u) * TAPE_COL;
+            const double dx = tape_lds(pa) - tape_lds(pb), dy = tape_lds(pa + TAPE_COL) - tape_lds(pb + TAPE_COL),
+                         dz = tape_lds(pa + 2 * TAPE_COL) - tape_lds(pb + 2 * TAPE_COL);
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            const unsigned kind = word >> 16;
+            tape_sts(xs_t + n * TAPE_COL, exp(-mbpol_par.k3[kind] * (d - mbpol_par.d3[kind])));
+            if (n >= 33) tape_sts(rs_t + (n - 6) * TAPE_COL, d);
+        }
+    }
+    double gab, gac, gbc;
+    const double sab = switch_fn(tape_lds(rs_t + 27 * TAPE_COL), mbpol_par.r3i, mbpol_par.r3f, gab);
+    const double sac = switch_fn(tape_lds(rs_t + 28 * TAPE_COL), mbpol_par.r3i, mbpol_par.r3f, gac);
+    const double sbc = switch_fn(tape_lds(rs_t + 29 * TAPE_COL), mbpol_par.r3i, mbpol_par.r3f, gbc);
+    sw[0] = sab * sac + sab * sbc + sac * sbc;
+    sw[1] = gab * (sac + sbc);
+    sw[2] = gac * (sab + sbc);
+    sw[3] = gbc * (sab + sac);
+}
+
 // The record phase 1 leaves per trimer (MBPOL_REC3 doubles): rec[n] = -k_n (dEpoly/dx_n s) x_n for the 36 variables,
 // rec[36] = s Epoly (the 3B energy, kcal/mol), rec[37..39] = Epoly ds/dr_OO.  Phase 2 (k_trimers_gather) only multiplies by
 // 1/d_n:  cv[n] = rec[n] / d_n (+ rec[37 + n - 33] / d_n for the three O-O variables) -- trimer_finish split in two.

@@ -43,7 +43,15 @@ __constant__ unsigned c_fat_segs2b[FAT2B_NSEGS];
 __constant__ unsigned c_fat_segs3b[FAT3B_NSEGS];
 __constant__ int c_fat_chunks2b[FAT2B_NCHUNKS + 1][3];
 __constant__ int c_fat_chunks3b[FAT3B_NCHUNKS + 1][3];
-__constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
+__constant__ unsigned c_v3word[36] = {      // compact prologue of k_trimers<4> (sym_stage_x): 3 * V3A[n] | 3 * V3B[n] << 8 | V3K[n] << 16
+#define W3(a, b, k) (3u * a | (3u * b) << 8 | (unsigned)k << 16)
+    W3(1, 2, 0), W3(4, 5, 0), W3(7, 8, 0), W3(0, 1, 1), W3(0, 2, 1), W3(3, 4, 1), W3(3, 5, 1), W3(6, 7, 1), W3(6, 8, 1),
+    W3(1, 4, 2), W3(1, 5, 2), W3(1, 7, 2), W3(1, 8, 2), W3(2, 4, 2), W3(2, 5, 2), W3(2, 7, 2), W3(2, 8, 2), W3(4, 7, 2), W3(4, 8, 2), W3(5, 7, 2), W3(5, 8, 2),
+    W3(0, 4, 3), W3(0, 5, 3), W3(0, 7, 3), W3(0, 8, 3), W3(3, 1, 3), W3(3, 2, 3), W3(3, 7, 3), W3(3, 8, 3), W3(6, 1, 3), W3(6, 2, 3), W3(6, 4, 3), W3(6, 5, 3),
+    W3(0, 3, 4), W3(0, 6, 4), W3(3, 6, 4)
+#undef W3
+};
+__constant__ unsigned c_sym_rowvars3b[SYM3B_NROWS * SYM3B_K + SYM_ROWVARS_SPARE];
 __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
 __constant__ int c_gather_vp[3][36];

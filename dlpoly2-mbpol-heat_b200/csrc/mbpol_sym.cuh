@@ -17,7 +17,7 @@
 
 // own staging buffers: the chunk size of this engine is independent of engines 1 and 3 (smaller chunks leave room for more
 // per-thread columns, i.e. more warps per SM)
-extern __constant__ unsigned c_sym_rowvars3b[(SYM3B_NROWS + 1) * SYM3B_K];
+extern __constant__ unsigned c_sym_rowvars3b[SYM3B_NROWS * SYM3B_K + SYM_ROWVARS_SPARE];
 extern __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 extern __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
 
@@ -28,6 +28,8 @@ struct SymSmem {
 };
 
 // x -> E = poly(x), g = dE/dx.  Must be called by ALL threads of a TAPE_BS-wide CTA (it contains barriers).
+// XSTAGED: the x columns were already filled by the caller (sym_stage_x in mbpol_device.cuh); x[] is read back from them.
+template <bool XSTAGED = false>
 __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, double (&x)[36], double (&g)[36], double& E, SymSmem& sm)
 {
     constexpr int NV = 36;
@@ -38,7 +40,8 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
     const unsigned gs_delta = (unsigned)sizeof(sm.xs);
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
-        tape_sts(xs_t + c * TAPE_COL, x[c]);
+        if (XSTAGED) x[c] = tape_lds(xs_t + c * TAPE_COL);
+        else tape_sts(xs_t + c * TAPE_COL, x[c]);
         tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
         g[c] = 0.0;
     }
@@ -63,6 +66,7 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         unsigned cp = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
         const unsigned row1 = c_sym_chunks3b[k + 1][1];
         SYM_ROW_DECL
+        SYM_ROW_WORDS(c_sym_chunks3b[k][1])
         SYM_ROW_FETCH(c_sym_chunks3b[k][1])
 #pragma unroll 1
         for (unsigned row = c_sym_chunks3b[k][1]; row < row1; ++row) {

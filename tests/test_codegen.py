@@ -170,3 +170,68 @@ def test_symmetry_batched_rows_reproduce_the_3b_polynomial(oracle, group):
     Er, gr = oracle.poly("3b", a, x)
     assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
     assert np.abs(g[:nv] - gr).max() <= 1e-11 * np.abs(gr).max()
+
+
+SYM_HOST_HARNESS = r"""
+// host emulation of csrc/mbpol_sym.cuh's row loop around the GENERATED header: shared memory is a byte array, one "thread"
+#include <cmath>
+#include <cstring>
+#include <vector>
+static unsigned char SM[1 << 21];
+static inline double tape_lds(unsigned a) { double v; std::memcpy(&v, SM + a, 8); return v; }
+static inline void tape_sts(unsigned a, double v) { std::memcpy(SM + a, &v, 8); }
+#define TAPE_LDS_V2(vx, vy, addr, imm) { vx = tape_lds((addr) + (imm)); vy = tape_lds((addr) + (imm) + 8); }
+#define SYM_FMA(acc, a, b) acc = std::fma(a, b, acc)
+#define TAPE_COL 8
+using std::fma;
+#include "sym_3b.h"
+extern "C" double sym_host_eval(const double* a, const double* xin, double* gout)
+{
+    const unsigned* rowvars = SYM3B_ROWVARS_HOST;
+    const unsigned xs_t = 64, gs_delta = 37 * 8, buf0 = 4096;
+    double x[36], g[36];
+    for (int c = 0; c < 36; ++c) { x[c] = xin[c]; g[c] = 0.0; tape_sts(xs_t + c * TAPE_COL, x[c]); tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0); }
+    tape_sts(xs_t + 36 * TAPE_COL, 1.0); tape_sts(xs_t + gs_delta + 36 * TAPE_COL, 0.0);
+    for (int i = 0; i < SYM3B_NTAPE; ++i)
+        tape_sts(buf0 + 8 * i, SYM3B_COEFIDX_HOST[i] < 0 ? 0.0 : a[SYM3B_COEFIDX_HOST[i]] * (double)SYM3B_COEFNUM_HOST[i] / (double)SYM3B_K);
+    double e = 0.0;
+    for (int k = 0; k < SYM3B_NCHUNKS; ++k) {
+        unsigned cp = buf0 + 8 * SYM3B_CHUNKS_HOST[k][2];
+        const unsigned row1 = SYM3B_CHUNKS_HOST[k + 1][1];
+        SYM_ROW_DECL
+        SYM_ROW_WORDS(SYM3B_CHUNKS_HOST[k][1])
+        SYM_ROW_FETCH(SYM3B_CHUNKS_HOST[k][1])
+        for (unsigned row = SYM3B_CHUNKS_HOST[k][1]; row < row1; ++row) {
+            SYM_ROW_PRE
+            SYM3B_ROW_SWITCH(shape)
+            SYM_ROW_POST
+        }
+    }
+    for (int c = 0; c < 36; ++c) gout[c] = g[c] + tape_lds(xs_t + gs_delta + c * TAPE_COL);
+    return e;
+}
+"""
+
+
+@pytest.mark.parametrize("env", [{}, {"SYM_POST": "serial", "SYM_WORDS_AHEAD": "0"}, {"SYM_GROUP": "s3"}])
+def test_generated_sym_header_on_the_host(tmp_path, oracle, env):
+    """The GENERATED header of engine 4 (macros included: row header prefetch, batched / serial row epilogue, alias flag, shape
+    dispatch) compiled for the host around an emulation of the shared-memory columns reproduces the oracle polynomial."""
+    hdr = tmp_path / "sym_3b.h"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_sym.py"), "--out", str(hdr)], env=dict(os.environ, **env),
+                          stdout=subprocess.DEVNULL)
+    (tmp_path / "h.cpp").write_text(SYM_HOST_HARNESS)
+    so = tmp_path / "libsymhost.so"
+    subprocess.check_call(["g++", "-O0", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(tmp_path), "-o", str(so), str(tmp_path / "h.cpp")])
+    lib = C.CDLL(str(so))
+    lib.sym_host_eval.restype = C.c_double
+    lib.sym_host_eval.argtypes = [C.c_void_p] * 3
+    a = np.ascontiguousarray(oracle.coef("3b"))
+    rng = np.random.default_rng(17)
+    for _ in range(3):
+        x = rng.uniform(0.1, 1.2, size=36)
+        g = np.zeros(36)
+        E = lib.sym_host_eval(a.ctypes.data, x.ctypes.data, g.ctypes.data)
+        Er, gr = oracle.poly("3b", a, x)
+        assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+        assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()

@@ -32,6 +32,8 @@ import gen_poly as G
 CHUNK = 2048
 DISPATCH = os.environ.get("SYM_DISPATCH", "if")
 ASMFMA = int(os.environ.get("SYM_ASMFMA", "0"))
+POST = os.environ.get("SYM_POST", "batch")        # row epilogue: "serial" (round-2 first form) | "batch" (all gradient-column loads first)
+WORDS_AHEAD = int(os.environ.get("SYM_WORDS_AHEAD", "1"))   # row words are read from constant memory this many rows before they are unpacked
 NV = 36
 UNIT = NV
 # atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
@@ -145,7 +147,9 @@ def emit(rows, shapes, vps, ahead, nsum):
         if (len(tape) - start) % 2:
             tape.append((-1, 0))
         assert len(tape) - start == slots_of(shapes[s])
-        rowvars.extend(w | (v << 8) | (s << 16) for (w, v) in key)      # row words: dynamic variables of every image + shape
+        cols = [c for wv in key for c in wv]
+        alias = 1 if len(set(cols)) < len(cols) else 0      # some dynamic column is updated twice by this super row: the epilogue must not batch its loads
+        rowvars.extend(w | (v << 8) | (s << 16) | (alias << 31) for (w, v) in key)      # row words: dynamic variables of every image + shape (+ alias flag)
     segs, chunks = [], []
     used, pos, cur = CHUNK + 1, 0, None
     for i, (s, key, children) in enumerate(rows):
@@ -211,24 +215,49 @@ def emit(rows, shapes, vps, ahead, nsum):
          "#define SYM%s_NV %d" % (Tg, NV), "#define SYM%s_K %d" % (Tg, K), "#define SYM%s_NROWS %d" % (Tg, len(rows)),
          "#define SYM%s_NTAPE %d" % (Tg, len(tape)), "#define SYM%s_NSEGS %d" % (Tg, len(segs)), "#define SYM%s_NCHUNKS %d" % (Tg, len(chunks) - 1),
          "#define SYM%s_NSHAPES %d" % (Tg, len(shapes)), "#define SYM%s_FP64_INSTR %d" % (Tg, nfp), "#define SYM_CHUNK_DOUBLES %d" % CHUNK]
-    rv = rowvars + rowvars[-K:]       # one spare super row: the header of the next row is prefetched
+    rv = rowvars + rowvars[-K:] * (1 + WORDS_AHEAD)      # spare super rows: the header of the next row(s) is prefetched
     L.append("static const unsigned SYM%s_ROWVARS_HOST[%d] = {%s};" % (Tg, len(rv), ",".join(str(w) for w in rv)))
     L.append("static const unsigned SYM%s_SEGS_HOST[%d] = {%s};" % (Tg, len(segs), ",".join(str(w) for w in segs)))
     L.append("// tape slot = coefficient index (< 0: zero) and numerator: value = a * num / |K|")
     L.append("static const short SYM%s_COEFIDX_HOST[%d] = {%s};" % (Tg, len(tape), ",".join(str(c) for c, n in tape)))
     L.append("static const unsigned char SYM%s_COEFNUM_HOST[%d] = {%s};" % (Tg, len(tape), ",".join(str(n) for c, n in tape)))
     L.append("static const int SYM%s_CHUNKS_HOST[%d][3] = {%s};" % (Tg, len(chunks), ",".join("{%d,%d,%d}" % c for c in chunks)))
-    # row header macros for K images
-    L.append("#define SYM_ROW_DECL unsigned nshape, %s; double %s;" % (", ".join("nw_%d, nv_%d" % (j, j) for j in range(K)), ", ".join("nxw_%d, nxv_%d" % (j, j) for j in range(K))))
-    L.append("#define SYM_ROW_FETCH(ROWIDX) { %s }" % " ".join(
-        "{ const unsigned vw_ = rowvars[(ROWIDX) * %d + %d]; %snw_%d = xs_t + (vw_ & 255u) * TAPE_COL; nv_%d = xs_t + ((vw_ >> 8) & 255u) * TAPE_COL; nxw_%d = tape_lds(nw_%d); nxv_%d = tape_lds(nv_%d); }"
-        % (K, j, "nshape = vw_ >> 16; " if j == 0 else "", j, j, j, j, j, j) for j in range(K)))
-    L.append("#define SYM_ROW_PRE const unsigned shape = nshape; %s SYM_ROW_FETCH(row + 1)" % " ".join(
+    L.append("#define SYM_ROWVARS_SPARE %d" % (K * (1 + WORDS_AHEAD)))
+    # row header macros for K images.  The header of the NEXT super row (row words -> column addresses -> the x values of its dynamic
+    # variables) is fetched while this row's body runs; with WORDS_AHEAD the row words themselves are read one row earlier
+    # still, so that the constant-memory latency is off the address computation.
+    jj = range(K)
+    L.append("#define SYM_ROW_DECL unsigned nshape, nalias, %s; double %s;%s" % (
+        ", ".join("nw_%d, nv_%d" % (j, j) for j in jj), ", ".join("nxw_%d, nxv_%d" % (j, j) for j in jj),
+        (" unsigned %s;" % ", ".join("rw_%d" % j for j in jj)) if WORDS_AHEAD else ""))
+    unpack = " ".join(
+        "{ %snw_%d = xs_t + (vw_%d & 255u) * TAPE_COL; nv_%d = xs_t + ((vw_%d >> 8) & 255u) * TAPE_COL; nxw_%d = tape_lds(nw_%d); nxv_%d = tape_lds(nv_%d); }"
+        % ("nshape = (vw_%d >> 16) & 0x7fffu; nalias = vw_%d >> 31; " % (j, j) if j == 0 else "", j, j, j, j, j, j, j, j) for j in jj)
+    if WORDS_AHEAD:
+        L.append("#define SYM_ROW_WORDS(ROWIDX) { %s }" % " ".join("rw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj))
+        L.append("#define SYM_ROW_FETCH(ROWIDX) { %s %s SYM_ROW_WORDS((ROWIDX) + 1) }" % (" ".join("const unsigned vw_%d = rw_%d;" % (j, j) for j in jj), unpack))
+    else:
+        L.append("#define SYM_ROW_WORDS(ROWIDX)")
+        L.append("#define SYM_ROW_FETCH(ROWIDX) { %s %s }" % (" ".join("const unsigned vw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj), unpack))
+    L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s SYM_ROW_FETCH(row + 1)" % " ".join(
         "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
-        % (j, j, j, j, j, j, j, j, j, j, j, j) for j in range(K)))
-    L.append("#define SYM_ROW_POST %s" % " ".join(
-        "e = fma(Tw_%d, p2_%d, e); tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
-        % (j, j, j, j, j, j, j, j, j, j) for j in range(K)))
+        % (j, j, j, j, j, j, j, j, j, j, j, j) for j in jj))
+    if POST == "serial":      # first form: six dependent load -> FMA -> store round trips (ptxas cannot reorder the possibly aliasing columns)
+        L.append("#define SYM_ROW_POST %s" % " ".join(
+            "e = fma(Tw_%d, p2_%d, e); tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
+            % (j, j, j, j, j, j, j, j, j, j) for j in jj))
+    else:
+        # batched: unless two of the 2|K| dynamic columns of the super row coincide (squares x_w^2, w_i = v_j, a variable fixed by
+        # an element of K; 18 of the 207 rows for K = z, flagged `alias` in the row word) all 2|K| loads go first, then the FMAs,
+        # then the stores -- one shared-memory round trip per row instead of 2|K| dependent ones.  Flagged rows stay serial.
+        ldw = " ".join("const double gw_%d = tape_lds(aw_%d + gs_delta);" % (j, j) for j in jj)
+        ldv = " ".join("const double gv_%d = tape_lds(av_%d + gs_delta);" % (j, j) for j in jj)
+        stw = " ".join("tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, gw_%d));" % (j, j, j, j) for j in jj)
+        stv = " ".join("tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, gv_%d));" % (j, j, j, j) for j in jj)
+        ee = " ".join("e = fma(Tw_%d, p2_%d, e);" % (j, j) for j in jj)
+        serial = " ".join("tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
+                          % (j, j, j, j, j, j, j, j) for j in jj)
+        L.append("#define SYM_ROW_POST if (!alias) { %s %s %s %s %s } else { %s %s }" % (ldw, ldv, ee, stw, stv, ee, serial))
     if DISPATCH == "switch":      # one loop over the super rows, dispatch inside (see tools/gen_fat.py); jump table instead of a compare tree
         L.append("#define SYM%s_ROW_SWITCH(shape) switch (shape) { \\" % Tg)
         for s in sorted(shapes):
