@@ -420,10 +420,12 @@ def main():
         v[...] = 0.0
     stress[...] = 0.0
     barrier()
-    te = []
+    te, hp = [], []
     for _ in range(args.steps):
         dt, res = e2e_step()
         te.append(dt)
+        hp.append(mb.mbpol_phase_times(h))
+    host_ms = {k[5:-3]: float(np.mean([q[k] for q in hp])) for k in ("host_upload_ms", "host_compute_ms", "host_download_ms")}
     barrier()
     clocks = sampler.stop() if rank == 0 else None      # sampled over the device-timed AND the end-to-end region
     t_e2e = torch.tensor([float(np.mean(te))], dtype=torch.float64, device="cuda")
@@ -457,7 +459,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(box, args, nd, nt),
                 "e2e": {"value": nt / float(t_e2e.item()), "unit": UNIT, "ms_per_step": 1e3 * float(t_e2e.item()),
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_ms_rank0": host_ms,
                         "note": "mbpol_b200_forces with pinned host arrays; per rank: H2D of coordinates + velocities, step, D2H + '+=' of "
                                 "this rank's slice of the reduced per-atom arrays"},
                 "gpu_launches": launches,
@@ -467,7 +469,7 @@ def main():
                                             "`clocks`; MEASURED_PEAKS.json has no FP64 entry",
                              "algorithmic_flop_per_trimer": mb.FLOP_PER_TRIMER,
                              "step_frac": step_flops / (ms_step * 1e-3) * 1e-12 / peak / world},
-                "phases_ms": {k: float(np.mean([q[k] for q in k3])) for k in k3[0]},
+                "phases_ms": {k: float(np.mean([q[k] for q in k3])) for k in k3[0] if not k.startswith("host_")},
                 "clocks": clocks}
         check = {"eng2": res["eng2"], "eng3": res["eng3"]}
         if world == 1 and not args.no_cpu_baseline:

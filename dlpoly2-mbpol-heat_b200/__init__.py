@@ -190,9 +190,10 @@ def mbpol_shard(h):
 
 
 def mbpol_phase_times(h):
-    ms = (C.c_float * 8)()
-    _check(h, load_library().mbpol_b200_phase_times(h.ptr, ms, C.c_int(8)), "mbpol_b200_phase_times")
-    keys = ("lists_ms", "k2b_ms", "k3b_ms", "total_ms", "k_trimers_ms", "gather_ms", "reduce_ms", "incidence_ms")
+    ms = (C.c_float * 11)()
+    _check(h, load_library().mbpol_b200_phase_times(h.ptr, ms, C.c_int(11)), "mbpol_b200_phase_times")
+    keys = ("lists_ms", "k2b_ms", "k3b_ms", "total_ms", "k_trimers_ms", "gather_ms", "reduce_ms", "incidence_ms",
+            "host_upload_ms", "host_compute_ms", "host_download_ms")
     return {k: float(ms[i]) for i, k in enumerate(keys)}
 
 

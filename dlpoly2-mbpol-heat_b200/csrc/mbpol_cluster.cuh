@@ -208,6 +208,7 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
     const int lane = threadIdx.x & 31;
     const bool active = w < nw;
     const int beg = active ? inc_off[w] : 0, end = active ? inc_off[w + 1] : 0;
+    if (!__syncthreads_or(end > beg)) return;      // no water of this block occurs in the shard's lists (most blocks of a multi-GPU run)
     const bool want_e = flags & MBPOL_B200_WANT_ATOMIC_ENERGY, want_w = flags & MBPOL_B200_WANT_FDECOMP, want_s = flags & MBPOL_B200_WANT_ATOMIC_STRESS;
     const double eu = MBPOL_ENGUNIT;
     double G[9], A[27], S[18], sc[8], esum = 0.0;     // G = sum g (kcal/mol/A); A = sum X_c (x) g; S; scalars E, vir, stress(6)
@@ -332,21 +333,41 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
     block_reduce_add_bead<9>(st, O.scal, S_STRESS, bead);
 }
 
-// incidence lists: water -> (trimer << 2 | slot) for the trimers [0, ntri) of this shard
+// incidence lists: water -> (trimer << 2 | slot) for the trimers [0, ntri) of this shard.  Consecutive list entries share their
+// centre water (the enumeration emits a water's clusters together), so the lanes of a warp that hit the same water are
+// aggregated first (__match_any_sync): one atomic per distinct water and warp instead of one per entry.
 template <int M>      // M = 3: trimers (int[3]), M = 2: dimers (int2)
 __global__ void k_inc_count(const long long* __restrict__ pcount, const int* __restrict__ tri, int* __restrict__ cnt)
 {
     const long long n3 = M * *pcount;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) atomicAdd(&cnt[tri[i]], 1);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n3; i0 += stride) {      // (block-uniform trip count)
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n3;
+        const int w = live ? tri[i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, w);
+        if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[w], __popc(peers));
+    }
 }
 template <int M>
 __global__ void k_inc_fill(const long long* __restrict__ pcount, const int* __restrict__ tri, const int* __restrict__ off, int* __restrict__ cur,
                            unsigned* __restrict__ inc)
 {
     const long long n3 = M * *pcount;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
-        const int w = tri[i];
-        inc[off[w] + atomicAdd(&cur[w], 1)] = M == 3 ? ((unsigned)((i / 3) << 2) | (unsigned)(i % 3)) : ((unsigned)((i / 2) << 1) | (unsigned)(i % 2));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n3; i0 += stride) {
+        const long long i = i0 + threadIdx.x;
+        const bool live = i < n3;
+        const int w = live ? tri[i] : -1;
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned peers = __match_any_sync(0xffffffffu, w);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (live && lane == (unsigned)leader) base = atomicAdd(&cur[w], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live)
+            inc[off[w] + base + __popc(peers & ((1u << lane) - 1u))] =
+                M == 3 ? ((unsigned)((i / 3) << 2) | (unsigned)(i % 3)) : ((unsigned)((i / 2) << 1) | (unsigned)(i % 2));
     }
 }
 
@@ -430,6 +451,7 @@ k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restr
     const int lane = threadIdx.x & 31;
     const bool active = w < nw;
     const int beg = active ? inc_off[w] : 0, end = active ? inc_off[w + 1] : 0;
+    if (!__syncthreads_or(end > beg)) return;      // no water of this block occurs in the shard's lists (most blocks of a multi-GPU run)
     const bool want_e = flags & MBPOL_B200_WANT_ATOMIC_ENERGY, want_w = flags & MBPOL_B200_WANT_FDECOMP, want_s = flags & MBPOL_B200_WANT_ATOMIC_STRESS;
     const double eu = MBPOL_ENGUNIT;
     double G[9], A[27], S[27], sc[8], esum = 0.0;

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "mbpol_b200.h"
@@ -569,7 +570,7 @@ struct mbpol_b200_handle {
     ncclComm_t comm = nullptr;
     int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
-    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ms[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // 0..7: device phases (events), 8..10: host wall time of upload / compute / download in the last mbpol_b200_forces
     // packed output buffer: [22 per-atom arrays of mxatms | pad to nranks equal chunks | NSCAL scalars per bead]
     size_t atom_count() const { return (size_t)22 * mxatms; }
     size_t chunk() const { const size_t c = (atom_count() + nranks - 1) / nranks; return (c + 1) & ~(size_t)1; }
@@ -1179,9 +1180,16 @@ int mbpol_b200_forces(mbpol_b200_handle* h, int imcon, const double* cell, int n
         h->err = "jflux requested without velocities (vxx, vyy, vzz)";
         return MBPOL_B200_EINVAL;
     }
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<float, std::milli>(clk::now() - t).count(); };
+    clk::time_point t0 = clk::now();
     if (int rc = mbpol_b200_upload(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, vxx, vyy, vzz)) return rc;
+    h->ms[8] = ms_since(t0); t0 = clk::now();
     if (int rc = mbpol_b200_compute(h)) return rc;
-    return mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+    h->ms[9] = ms_since(t0); t0 = clk::now();
+    const int rc = mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+    h->ms[10] = ms_since(t0);
+    return rc;
 }
 
 int mbpol_b200_forces_batched(mbpol_b200_handle* h, int nbeads, int imcon, const double* cell, int nttm2, const int* listttm2, int mxatms,
@@ -1234,7 +1242,7 @@ int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches
 int mbpol_b200_phase_times(mbpol_b200_handle* h, float* ms, int n)
 {
     if (!h || !ms || n < 0) return MBPOL_B200_EINVAL;
-    for (int k = 0; k < n; ++k) ms[k] = k < 8 ? h->ms[k] : 0.f;
+    for (int k = 0; k < n; ++k) ms[k] = k < 11 ? h->ms[k] : 0.f;
     return MBPOL_B200_OK;
 }
 

@@ -140,8 +140,9 @@ int mbpol_b200_counts(mbpol_b200_handle* handle, long long* n_dimers_total, long
 int mbpol_b200_get_lists(mbpol_b200_handle* handle, int* dimers /*2*n*/, long long dimer_cap,
                          int* trimers /*3*n*/, long long trimer_cap);   /* 0-based water indices, i<j(<k), full lists */
 int mbpol_b200_kernel_times(mbpol_b200_handle* handle, float* ms /*[4]: lists, 2B, 3B, total*/, long long* launches);
-/* finer split, n <= 8: 0 lists, 1 2B, 2 3B (incidence lists + k_trimers + gather), 3 whole step incl. reduction, 4 k_trimers alone
- * (the roofline kernel), 5 k_trimers_gather, 6 reduction over the ranks, 7 incidence lists */
+/* finer split, n <= 11: 0 lists, 1 2B, 2 3B (incidence lists + k_trimers + gather), 3 whole step incl. reduction, 4 k_trimers alone
+ * (the roofline kernel), 5 k_trimers_gather, 6 reduction over the ranks, 7 incidence lists (device time, CUDA events);
+ * 8 upload, 9 compute, 10 download: host wall time of the three parts of the last mbpol_b200_forces call */
 int mbpol_b200_phase_times(mbpol_b200_handle* handle, float* ms, int n);
 
 /* FP64 roofline probe: best-of-3 throughput of independent register-resident DFMA chains on the current device

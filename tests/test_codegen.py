@@ -213,7 +213,7 @@ extern "C" double sym_host_eval(const double* a, const double* xin, double* gout
 """
 
 
-@pytest.mark.parametrize("env", [{}, {"SYM_POST": "serial", "SYM_WORDS_AHEAD": "0"}, {"SYM_GROUP": "s3"}])
+@pytest.mark.parametrize("env", [{}, {"SYM_POST": "serial", "SYM_WORDS_AHEAD": "0"}, {"SYM_POST": "batch"}, {"SYM_GROUP": "s3"}])
 def test_generated_sym_header_on_the_host(tmp_path, oracle, env):
     """The GENERATED header of engine 4 (macros included: row header prefetch, batched / serial row epilogue, alias flag, shape
     dispatch) compiled for the host around an emulation of the shared-memory columns reproduces the oracle polynomial."""

@@ -32,8 +32,12 @@ import gen_poly as G
 CHUNK = 2048
 DISPATCH = os.environ.get("SYM_DISPATCH", "if")
 ASMFMA = int(os.environ.get("SYM_ASMFMA", "0"))
-POST = os.environ.get("SYM_POST", "batch")        # row epilogue: "serial" (round-2 first form) | "batch" (all gradient-column loads first)
+POST = os.environ.get("SYM_POST", "inbody")       # row epilogue: "serial" (round-2 first form) | "batch" (all gradient-column loads first) | "inbody" (batch, inside the shape bodies)
 WORDS_AHEAD = int(os.environ.get("SYM_WORDS_AHEAD", "1"))   # row words are read from constant memory this many rows before they are unpacked
+# trie order and representative rule found by tools/search_sym_order.py for K = z (J = FP64 instructions + 0.28 * leaf pairs of code):
+# 73 920 instructions per trimer, 138 super rows of 52 shapes, 9 495 leaf pairs of code (orbit order reversed: 79 791 / 207 / 61 / 9 408)
+DEFAULT_ORDER = "1,2,0,11,8,7,10,9,4,5,6,3"
+DEFAULT_REPSEL = "min"
 NV = 36
 UNIT = NV
 # atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
@@ -74,14 +78,22 @@ def orbit_order(vps):
     return order
 
 
-def build(mono, group="z", reverse=True, repsel="max"):
+def build(mono, group="z", reverse=True, repsel="max", order=None):
     """-> (super rows, shapes, vps).  super row = (shape id, [(w_j, v_j)], children); child = (us, own, leaves) with
     us = (u_j), own = (coef index, num) or None, leaves = [((c_j), coef index, num)]; the tape value is a * num / |K|."""
     vps = [varperm(molperm(p)) for p in GROUPS[group]]
     K = len(vps)
-    order = orbit_order(vps)
-    if reverse:
-        order = order[::-1]
+    if order is None:
+        order = orbit_order(vps)
+        if reverse:
+            order = order[::-1]
+    else:      # explicit trie order: a permutation of the K-orbits of variables (tools/search_sym_order.py)
+        orbs = orbit_order(vps)
+        n = len(vps)
+        blocks = [orbs[i:i + n] for i in range(0, len(orbs), n)]
+        assert all(len(set(vp[v] for vp in vps)) == n for v in range(NV)), "explicit orders need a group without fixed variables"
+        order = [v for b in order for v in blocks[b]]
+        assert sorted(order) == list(range(NV))
     rank = {v: i for i, v in enumerate(order)}
     monos = {}
     for r in mono:
@@ -131,6 +143,13 @@ def build(mono, group="z", reverse=True, repsel="max"):
     return out, {s: sh for sh, s in shapes.items()}, vps
 
 
+def stats(rows, shapes, K):
+    """(FP64 instructions per cluster, leaf pairs of code, super rows, shapes) of a schedule"""
+    nfp = sum(K * (4 + sum(2 * len(ls) + (4 if us[0] != UNIT else 1) for us, own, ls in ch)) for s, key, ch in rows)
+    code = sum(sum(len(ls) for us, ls in sh) for sh in shapes.values()) * K
+    return nfp, code, len(rows), len(shapes)
+
+
 def slots_of(shape):
     n = sum(1 + len(ls) for us, ls in shape)
     return n + (n % 2)
@@ -167,6 +186,19 @@ def emit(rows, shapes, vps, ahead, nsum):
     chunks.append((len(segs), len(rows), len(tape)))
     nfp = 0
     body_of = {}
+    jj = range(K)
+    shape_alias = collections.defaultdict(set)
+    for (s, key, children) in rows:
+        cols = [c for wv in key for c in wv]
+        shape_alias[s].add(len(set(cols)) < len(cols))
+    # row epilogue pieces (see the POST comment further down)
+    ldw = " ".join("const double gw_%d = tape_lds(aw_%d + gs_delta);" % (j, j) for j in jj)
+    ldv = " ".join("const double gv_%d = tape_lds(av_%d + gs_delta);" % (j, j) for j in jj)
+    stw = " ".join("tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, gw_%d));" % (j, j, j, j) for j in jj)
+    stv = " ".join("tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, gv_%d));" % (j, j, j, j) for j in jj)
+    ee = " ".join("e = fma(Tw_%d, p2_%d, e);" % (j, j) for j in jj)
+    serial = " ".join("tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
+                      % (j, j, j, j, j, j, j, j) for j in jj)
     for s, shape in shapes.items():
         body, off = [], 0
         npairs = slots_of(shape) // 2
@@ -183,7 +215,10 @@ def emit(rows, shapes, vps, ahead, nsum):
             load_upto(pair + 1 + ahead)
             return "q%d%s" % (pair, "xy"[lane])
         load_upto(ahead)
+        hoist = POST == "inbody" and shape_alias[s] == {False}
         for k, (us, ls) in enumerate(shape):
+            if hoist and k == len(shape) - 1:      # gradient columns of the dynamic variables: loaded a whole child ahead of their use
+                body.append(ldw + " " + ldv)
             own = slot(off)
             for j in range(K):
                 if us[j] != UNIT:
@@ -207,6 +242,13 @@ def emit(rows, shapes, vps, ahead, nsum):
                 else:
                     body.append("{ const double S_ = %s; g[%d] = fma(S_, p2_%d, g[%d]); Tw_%d = fma(S_, x[%d], Tw_%d); }" % (ssum, us[j], j, us[j], j, us[j], j))
             off += 1 + len(ls)
+        if POST == "inbody":
+            if hoist:
+                body.append("%s %s %s" % (ee, stw, stv))
+            elif shape_alias[s] == {True}:
+                body.append("%s %s" % (ee, serial))
+            else:
+                body.append("%s if (alias) { %s } else { %s %s %s %s }" % (ee, serial, ldw, ldv, stw, stv))
         body_of[s] = " ".join(body)
     for (s, key, children) in rows:
         nfp += K * (4 + sum(2 * len(ls) + (4 if us[0] != UNIT else 1) for us, own, ls in children))
@@ -239,10 +281,20 @@ def emit(rows, shapes, vps, ahead, nsum):
     else:
         L.append("#define SYM_ROW_WORDS(ROWIDX)")
         L.append("#define SYM_ROW_FETCH(ROWIDX) { %s %s }" % (" ".join("const unsigned vw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj), unpack))
-    L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s SYM_ROW_FETCH(row + 1)" % " ".join(
+    if POST == "inbody":
+        # the epilogue lives in the shape bodies; the header of the next row is fetched AFTER the body (its x loads fly during the
+        # dispatch of the next row), straight into the registers the next row reads: no double-buffered header, no register moves
+        L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s" % " ".join(
+            "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
+            % (j, j, j, j, j, j, j, j, j, j, j, j) for j in jj))
+        L.append("#define SYM_ROW_POST SYM_ROW_FETCH(row + 1)")
+    else:
+      L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s SYM_ROW_FETCH(row + 1)" % " ".join(
         "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
         % (j, j, j, j, j, j, j, j, j, j, j, j) for j in jj))
-    if POST == "serial":      # first form: six dependent load -> FMA -> store round trips (ptxas cannot reorder the possibly aliasing columns)
+    if POST == "inbody":
+        pass
+    elif POST == "serial":      # first form: six dependent load -> FMA -> store round trips (ptxas cannot reorder the possibly aliasing columns)
         L.append("#define SYM_ROW_POST %s" % " ".join(
             "e = fma(Tw_%d, p2_%d, e); tape_sts(aw_%d + gs_delta, fma(Tw_%d, xv_%d, tape_lds(aw_%d + gs_delta))); tape_sts(av_%d + gs_delta, fma(Tw_%d, xw_%d, tape_lds(av_%d + gs_delta)));"
             % (j, j, j, j, j, j, j, j, j, j) for j in jj))
@@ -277,8 +329,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=os.environ.get("SYM_GROUP", "z"), choices=sorted(GROUPS))
     ap.add_argument("--forward", action="store_true", help="trie order = orbit order (default: reversed)")
-    ap.add_argument("--repsel", default=os.environ.get("SYM_REPSEL", "max"), choices=["max", "min"])
-    ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "12")))
+    ap.add_argument("--repsel", default=os.environ.get("SYM_REPSEL", DEFAULT_REPSEL), choices=["max", "min"])
+    ap.add_argument("--order", default=os.environ.get("SYM_ORDER", DEFAULT_ORDER), help="trie order: comma-separated permutation of the K-orbits of variables ('' = --forward / reversed orbit order)")
+    ap.add_argument("--ahead", type=int, default=int(os.environ.get("SYM_AHEAD", "6")))
     ap.add_argument("--nsum", type=int, default=int(os.environ.get("SYM_NSUM", "1")))
     ap.add_argument("--dispatch", default=DISPATCH, choices=["if", "switch"])
     ap.add_argument("--asmfma", type=int, default=ASMFMA)
@@ -291,7 +344,8 @@ def main():
     globals()["CHUNK"] = args.chunk
     globals()["DISPATCH"] = ap_dispatch
     globals()["ASMFMA"] = args.asmfma
-    rows, shapes, vps = build(d["mono3b"], args.group, not args.forward, args.repsel)
+    order = [int(v) for v in args.order.split(",")] if args.order and args.group == "z" else None
+    rows, shapes, vps = build(d["mono3b"], args.group, not args.forward, args.repsel, order=order)
     txt, nfp, nseg, nch, ntape = emit(rows, shapes, vps, args.ahead, args.nsum)
     open(args.out, "w").write(txt)
     code = sum(sum(len(ls) for us, ls in sh) for sh in shapes.values()) * len(vps)
