@@ -124,6 +124,40 @@ __device__ __forceinline__ void trimer_geometry(int nw, const double* __restrict
     }
 }
 
+// water-major copy (k_gather_image): nine coordinates + the raw coordinate sum of the water, six 16-byte loads
+__device__ __forceinline__ void load_water_aos(const double* __restrict__ monoA, int m, double (&w)[9], double (&X)[3])
+{
+    const double2* A = reinterpret_cast<const double2*>(monoA + (size_t)m * 12);
+    const double2 a0 = __ldg(A), a1 = __ldg(A + 1), a2 = __ldg(A + 2), a3 = __ldg(A + 3), a4 = __ldg(A + 4), a5 = __ldg(A + 5);
+    w[0] = a0.x; w[1] = a0.y; w[2] = a1.x; w[3] = a1.y; w[4] = a2.x; w[5] = a2.y; w[6] = a3.x; w[7] = a3.y; w[8] = a4.x;
+    X[0] += a4.y; X[1] += a5.x; X[2] += a5.y;
+}
+// trimer_geometry from the water-major copy; X += raw coordinate sum of the nine atoms
+__device__ __forceinline__ void trimer_geometry_aos(const double* __restrict__ monoA, const CellInfo& C, int mi, int mj, int mk, double (&r)[27], double (&X)[3])
+{
+    double wj[9], wi[9], wk[9];
+    load_water_aos(monoA, mi, wi, X);
+    load_water_aos(monoA, mj, wj, X);
+    load_water_aos(monoA, mk, wk, X);
+    double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+    double b0 = wj[0] - wk[0], b1 = wj[1] - wk[1], b2 = wj[2] - wk[2];
+    image_vec(C, a0, a1, a2);
+    image_vec(C, b0, b1, b2);
+    const double ra[3] = {a0, a1, a2}, rb[3] = {b0, b1, b2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[c] = ra[c];
+        r[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+        r[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+        r[9 + c] = 0.0;
+        r[12 + c] = wj[3 + c] - wj[c];
+        r[15 + c] = wj[6 + c] - wj[c];
+        r[18 + c] = -rb[c];
+        r[21 + c] = (wk[3 + c] - wk[c]) - rb[c];
+        r[24 + c] = (wk[6 + c] - wk[c]) - rb[c];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K3 phase 1: one thread per accepted trimer of this shard -- geometry, variables, switch, polynomial (the tape walk) and
 // a 40-double RECORD per trimer (trimer_record); nothing is scattered here.  The records of a CTA are staged through the
@@ -224,8 +258,8 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
         const unsigned code = inc[i];
         const int t = (int)(code >> 2), s = (int)(code & 3u);
         const int m3[3] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
-        double r0[27], r[27];
-        trimer_geometry(nw, mono, C, m3[0], m3[1], m3[2], r0);
+        double r0[27], r[27], X[3] = {0.0, 0.0, 0.0};
+        trimer_geometry_aos(mono, C, m3[0], m3[1], m3[2], r0, X);
         // relabel: molecule 0 <-> molecule s
 #pragma unroll
         for (int m = 0; m < 3; ++m)
@@ -272,14 +306,7 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
             sc[2] -= r[3 * a] * gx; sc[3] -= r[3 * a] * gy; sc[4] -= r[3 * a] * gz;
             sc[5] -= r[3 * a + 1] * gy; sc[6] -= r[3 * a + 1] * gz; sc[7] -= r[3 * a + 2] * gz;
         }
-        if (want_w) {   // X_c = sum of the RAW coordinates of the 9 atoms of the cluster
-            double X[3] = {0, 0, 0};
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const int o = list[3 * m3[m]] - 1;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { X[0] += xr[o + k]; X[1] += yr[o + k]; X[2] += zr[o + k]; }
-            }
+        if (want_w) {   // X_c = sum of the RAW coordinates of the 9 atoms of the cluster (carried by the water-major copy)
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -401,6 +428,26 @@ __device__ __forceinline__ void dimer_geometry(int nw, const double* __restrict_
     }
 }
 
+// dimer_geometry from the water-major copy (k_gather_image); X += raw coordinate sum of the six atoms
+__device__ __forceinline__ void dimer_geometry_aos(const double* __restrict__ monoA, const CellInfo& C, int mi, int mj, double (&w)[18], double (&X)[3])
+{
+    double wi[9], wj[9];
+    load_water_aos(monoA, mi, wi, X);
+    load_water_aos(monoA, mj, wj, X);
+    double a0 = wi[0] - wj[0], a1 = wi[1] - wj[1], a2 = wi[2] - wj[2];
+    image_vec(C, a0, a1, a2);
+    const double ra[3] = {a0, a1, a2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        w[c] = ra[c];
+        w[3 + c] = (wi[3 + c] - wi[c]) + ra[c];
+        w[6 + c] = (wi[6 + c] - wi[c]) + ra[c];
+        w[9 + c] = 0.0;
+        w[12 + c] = wj[3 + c] - wj[c];
+        w[15 + c] = wj[6 + c] - wj[c];
+    }
+}
+
 template <int ENGINE>
 __global__ void __launch_bounds__(TAPE_BS, (256 / TAPE_BS) > 0 ? (256 / TAPE_BS) : 1)
 k_dimers(const long long* __restrict__ pcount, const int2* __restrict__ dim, int nw, const double* __restrict__ mono, CellInfo C,
@@ -465,8 +512,8 @@ k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restr
         const unsigned code = inc[i];
         const int t = (int)(code >> 1), s = (int)(code & 1u);
         const int2 m2 = dim[t];
-        double w0[18], wv[18];
-        dimer_geometry(nw, mono, C, m2.x, m2.y, w0);
+        double w0[18], wv[18], X[3] = {0.0, 0.0, 0.0};
+        dimer_geometry_aos(mono, C, m2.x, m2.y, w0, X);
 #pragma unroll
         for (int c = 0; c < 9; ++c) {       // relabel: the gathering water becomes molecule a
             wv[c] = s ? w0[9 + c] : w0[c];
@@ -516,13 +563,7 @@ k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restr
                     }
                 }
         }
-        if (want_w) {
-            double X[3] = {0, 0, 0};
-            const int oo[2] = {list[3 * m2.x] - 1, list[3 * m2.y] - 1};
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { X[0] += xr[oo[m] + k]; X[1] += yr[oo[m] + k]; X[2] += zr[oo[m] + k]; }
+        if (want_w) {      // X_c: raw coordinate sum of the six atoms (carried by the water-major copy)
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll

@@ -79,8 +79,10 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // K0: gather + image_monomers.  mono[c*nw + m], c = 0..8 (O xyz, H1 xyz, H2 xyz)
 // ---------------------------------------------------------------------------------------------------------
+// monoA[m][12]: the same nine coordinates water-major plus the RAW coordinate sum of the water's three atoms (o, o+1, o+2 as
+// do_dimer / do_trimer address them) -- 96 bytes = three sectors per water for the gather kernels, which visit waters at random
 __global__ void k_gather_image(int nw, const int* __restrict__ list, const double* __restrict__ x, const double* __restrict__ y,
-                               const double* __restrict__ z, CellInfo C, double* __restrict__ mono)
+                               const double* __restrict__ z, CellInfo C, double* __restrict__ mono, double* __restrict__ monoA)
 {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nw) return;
@@ -98,6 +100,11 @@ __global__ void k_gather_image(int nw, const int* __restrict__ list, const doubl
     }
 #pragma unroll
     for (int c = 0; c < 9; ++c) mono[(size_t)c * nw + m] = w[c];
+    const int o = list[3 * m] - 1;
+    double2* A = reinterpret_cast<double2*>(monoA + (size_t)m * 12);
+    A[0] = make_double2(w[0], w[1]); A[1] = make_double2(w[2], w[3]); A[2] = make_double2(w[4], w[5]); A[3] = make_double2(w[6], w[7]);
+    A[4] = make_double2(w[8], (x[o] + x[o + 1]) + x[o + 2]);
+    A[5] = make_double2((y[o] + y[o + 1]) + y[o + 2], (z[o] + z[o + 1]) + z[o + 2]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -549,7 +556,7 @@ struct mbpol_b200_handle {
     CellInfo C;
     Grid G;
     int ncells = 0;
-    DevBuf<double> xyz, vel, mono, out, rec, rec2;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
+    DevBuf<double> xyz, vel, mono, monoA, out, rec, rec2;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
     DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, unsorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur;
     DevBuf<unsigned> inc, inc2;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
@@ -887,6 +894,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     const int w0 = h->w0, nown = h->nown;
     const int gb = (nw + TB - 1) / TB, go = (nown + TB - 1) / TB;
     CUDA_TRY(h, h->mono.reserve(9 * (size_t)nw));
+    CUDA_TRY(h, h->monoA.reserve(12 * (size_t)nw));
     CUDA_TRY(h, h->out.reserve(h->out_alloc()));
     CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw)); CUDA_TRY(h, h->unsorted.reserve(nw));
     CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
@@ -911,7 +919,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, cudaMemsetAsync(h->cell_cnt.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->cell_fill.p, 0, (size_t)(h->ncells + 1) * 4, s));
     CUDA_TRY(h, cudaMemsetAsync(h->flag.p, 0, 4, s));
-    k_gather_image<<<gb, TB, 0, s>>>(nw, h->list.p, h->xyz.p, h->xyz.p + n, h->xyz.p + 2 * n, h->C, h->mono.p);
+    k_gather_image<<<gb, TB, 0, s>>>(nw, h->list.p, h->xyz.p, h->xyz.p + n, h->xyz.p + 2 * n, h->C, h->mono.p, h->monoA.p);
     k_cell_index<<<gb, TB, 0, s>>>(nw, h->mono.p, h->G, h->cell_id.p, h->cell_cnt.p);
     if (int rc = scan_int(h, h->cell_cnt.p, h->cell_cnt.p, h->ncells + 1)) return rc;   // in-place exclusive scan -> cell_start
     k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->unsorted.p);
@@ -976,7 +984,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
             k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_fat2b[h->device], h->rec2.p);
         else
             k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_tape2b[h->device], h->rec2.p);
-        k_dimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc2.p, h->dimers.p, h->rec2.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        k_dimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc2.p, h->dimers.p, h->rec2.p, h->monoA.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
         h->launches += 6;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
@@ -999,7 +1007,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         else
             k_trimers<1><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_tape3b[h->device], h->rec.p);
         CUDA_TRY(h, cudaEventRecord(h->ev[6], s));
-        k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, h->trimers.p, h->rec.p, h->mono.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+        k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, h->trimers.p, h->rec.p, h->monoA.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
         CUDA_TRY(h, cudaEventRecord(h->ev[7], s));
         h->launches += 6;
     } else {
