@@ -254,10 +254,24 @@ k_trimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __rest
     for (int i = 0; i < 18; ++i) S[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sc[i] = 0.0;
+    // the incidence code and the triple of the NEXT incidence of this lane are fetched while the current one is evaluated: one level
+    // of dependent loads (coordinates, record) per iteration instead of three
+    unsigned ncode = 0;
+    int nm[3] = {0, 0, 0};
+    if (beg + lane < end) {
+        ncode = inc[beg + lane];
+        const int t = (int)(ncode >> 2);
+        nm[0] = tri[3 * t]; nm[1] = tri[3 * t + 1]; nm[2] = tri[3 * t + 2];
+    }
     for (int i = beg + lane; i < end; i += 32) {
-        const unsigned code = inc[i];
+        const unsigned code = ncode;
         const int t = (int)(code >> 2), s = (int)(code & 3u);
-        const int m3[3] = {tri[3 * t], tri[3 * t + 1], tri[3 * t + 2]};
+        const int m3[3] = {nm[0], nm[1], nm[2]};
+        if (i + 32 < end) {
+            ncode = inc[i + 32];
+            const int tn = (int)(ncode >> 2);
+            nm[0] = tri[3 * tn]; nm[1] = tri[3 * tn + 1]; nm[2] = tri[3 * tn + 2];
+        }
         double r0[27], r[27], X[3] = {0.0, 0.0, 0.0};
         trimer_geometry_aos(mono, C, m3[0], m3[1], m3[2], r0, X);
         // relabel: molecule 0 <-> molecule s
@@ -508,10 +522,20 @@ k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restr
     for (int i = 0; i < 27; ++i) { A[i] = 0.0; S[i] = 0.0; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) sc[i] = 0.0;
+    unsigned ncode = 0;      // next incidence of this lane, fetched one iteration ahead (see k_trimers_gather)
+    int2 nm = make_int2(0, 0);
+    if (beg + lane < end) {
+        ncode = inc[beg + lane];
+        nm = dim[ncode >> 1];
+    }
     for (int i = beg + lane; i < end; i += 32) {
-        const unsigned code = inc[i];
+        const unsigned code = ncode;
         const int t = (int)(code >> 1), s = (int)(code & 1u);
-        const int2 m2 = dim[t];
+        const int2 m2 = nm;
+        if (i + 32 < end) {
+            ncode = inc[i + 32];
+            nm = dim[ncode >> 1];
+        }
         double w0[18], wv[18], X[3] = {0.0, 0.0, 0.0};
         dimer_geometry_aos(mono, C, m2.x, m2.y, w0, X);
 #pragma unroll
