@@ -45,6 +45,7 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0);
         g[c] = 0.0;
     }
+    SYM_PAIR_INIT                                          // pair sums y = x_c + x_c' and their gradient accumulators (tools/gen_sym.py, PAIRS)
     tape_sts(xs_t + NV * TAPE_COL, 1.0);
     tape_sts(xs_t + gs_delta + NV * TAPE_COL, 0.0);
     auto stage = [&](int k) {
@@ -76,6 +77,7 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }
+    SYM_PAIR_FINI
 #pragma unroll
     for (int c = 0; c < NV; ++c) g[c] += tape_lds(xs_t + gs_delta + c * TAPE_COL);
     E = e;

@@ -192,6 +192,7 @@ extern "C" double sym_host_eval(const double* a, const double* xin, double* gout
     double x[36], g[36];
     for (int c = 0; c < 36; ++c) { x[c] = xin[c]; g[c] = 0.0; tape_sts(xs_t + c * TAPE_COL, x[c]); tape_sts(xs_t + gs_delta + c * TAPE_COL, 0.0); }
     tape_sts(xs_t + 36 * TAPE_COL, 1.0); tape_sts(xs_t + gs_delta + 36 * TAPE_COL, 0.0);
+    SYM_PAIR_INIT
     for (int i = 0; i < SYM3B_NTAPE; ++i)
         tape_sts(buf0 + 8 * i, SYM3B_COEFIDX_HOST[i] < 0 ? 0.0 : a[SYM3B_COEFIDX_HOST[i]] * (double)SYM3B_COEFNUM_HOST[i] / (double)SYM3B_K);
     double e = 0.0;
@@ -207,13 +208,14 @@ extern "C" double sym_host_eval(const double* a, const double* xin, double* gout
             SYM_ROW_POST
         }
     }
+    SYM_PAIR_FINI
     for (int c = 0; c < 36; ++c) gout[c] = g[c] + tape_lds(xs_t + gs_delta + c * TAPE_COL);
     return e;
 }
 """
 
 
-@pytest.mark.parametrize("env", [{}, {"SYM_POST": "serial", "SYM_WORDS_AHEAD": "0"}, {"SYM_POST": "batch"}, {"SYM_GROUP": "s3"}])
+@pytest.mark.parametrize("env", [{}, {"SYM_POST": "serial", "SYM_WORDS_AHEAD": "0"}, {"SYM_POST": "batch", "SYM_PAIRS": "0"}, {"SYM_GROUP": "s3"}])
 def test_generated_sym_header_on_the_host(tmp_path, oracle, env):
     """The GENERATED header of engine 4 (macros included: row header prefetch, batched / serial row epilogue, alias flag, shape
     dispatch) compiled for the host around an emulation of the shared-memory columns reproduces the oracle polynomial."""

@@ -20,6 +20,8 @@ W_CODE = float(__import__("os").environ.get("SYM_W_CODE", "0.6"))      # refitte
 
 def J(mono, order, repsel):
     rows, shapes, vps = S.build(mono, "z", True, repsel, order=list(order))
+    if S.PAIRS:
+        rows, shapes = S.merge_pairs(rows)
     nfp, code, nrows, nshapes = S.stats(rows, shapes, len(vps))
     return nfp + W_CODE * code, (nfp, code, nrows, nshapes)
 
