@@ -70,7 +70,7 @@ class DeviceArray:
 
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks.mem")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -99,8 +99,16 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         load = [s for s in sm if mx and s > 0.5 * mx[0]] or sm
+        def col(k):
+            v = []
+            for r in self.rows:
+                try:
+                    v.append(float(r[k]))
+                except (ValueError, IndexError):
+                    pass
+            return float(np.median(v)) if v else None
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "mem_mhz": col(7), "power_w": col(2)}
 
 
 # ------------------------------------------------------------------------------------------------------------
