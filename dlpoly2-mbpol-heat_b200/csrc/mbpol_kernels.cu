@@ -551,7 +551,8 @@ struct mbpol_b200_handle {
     int mxatms = 0, imcon = 0;
     bool have_vel = false, uploaded = false;
     std::string err;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, vstream = nullptr;      // vstream: velocity upload (needed only by k_flux at the end of the step)
+    cudaEvent_t vel_ev = nullptr;
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CellInfo C;
     Grid G;
@@ -573,7 +574,7 @@ struct mbpol_b200_handle {
     struct HostBack { long long counts[4]; double tail[3]; int flag; int pad; } *back = nullptr;     // pinned: read back once per step
     double* host_weight_d = nullptr;           // pinned: per-water load-balancing weights of the previous step (all ranks)
     std::vector<int> host_weight;
-    bool have_weight = false;
+    bool have_weight = false, weights_pending = false;
     ncclComm_t comm = nullptr;
     int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
@@ -628,6 +629,8 @@ struct NcclApi {
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclReduceScatter) ReduceScatter = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     bool ok = false;
 };
@@ -646,7 +649,9 @@ const NcclApi& nccl_api()
         api.ReduceScatter = reinterpret_cast<decltype(api.ReduceScatter)>(dlsym(lib, "ncclReduceScatter"));
         api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.ReduceScatter && api.AllReduce && api.GetErrorString;
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.ReduceScatter && api.AllReduce && api.GetErrorString && api.GroupStart && api.GroupEnd;
     });
     return api;
 }
@@ -721,6 +726,8 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
         }
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    if (cudaStreamCreateWithFlags(&h->vstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->vel_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     if (cudaMallocHost(&h->back, sizeof(*h->back)) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     *handle = h;
@@ -739,6 +746,8 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     if (h->host_weight_d) cudaFreeHost(h->host_weight_d);
     for (cudaEvent_t e : h->dl_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
+    if (h->vstream) cudaStreamDestroy(h->vstream);
+    if (h->vel_ev) cudaEventDestroy(h->vel_ev);
     delete h;
     return MBPOL_B200_OK;
 }
@@ -751,7 +760,7 @@ int mbpol_b200_set_shard(mbpol_b200_handle* h, int rank, int nranks)
 {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks) return MBPOL_B200_EINVAL;
     if (h->comm && (rank != h->rank || nranks != h->nranks)) { h->err = "the shard of a handle with a communicator is fixed by mbpol_b200_comm_init"; return MBPOL_B200_EINVAL; }
-    if (rank != h->rank || nranks != h->nranks) { h->est_nd = h->est_nt = -1; h->have_weight = false; }
+    if (rank != h->rank || nranks != h->nranks) { h->est_nd = h->est_nt = -1; h->have_weight = h->weights_pending = false; }
     h->rank = rank; h->nranks = nranks;
     return MBPOL_B200_OK;
 }
@@ -774,7 +783,7 @@ int mbpol_b200_comm_init(mbpol_b200_handle* h, int rank, int nranks, const void*
     if (!nccl_api().ok) { h->err = "libnccl.so.2 not found (or too old): the in-library reduction needs NCCL"; return MBPOL_B200_ECUDA; }
     NCCL_TRY(h, nccl_api().CommInitRank(&h->comm, nranks, uid, rank));
     h->rank = rank; h->nranks = nranks;
-    h->est_nd = h->est_nt = -1; h->have_weight = false;
+    h->est_nd = h->est_nt = -1; h->have_weight = h->weights_pending = false;
     h->reduce_mode = nranks > 1 ? 2 : 0;
     return MBPOL_B200_OK;
 }
@@ -866,9 +875,11 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
     h->have_vel = vxx && vyy && vzz;
     if (h->have_vel) {
         CUDA_TRY(h, h->vel.reserve(3 * n));
-        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p, vxx, n * 8, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + n, vyy, n * 8, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + 2 * n, vzz, n * 8, cudaMemcpyHostToDevice, h->stream));
+        // on their own stream: the step only waits for them in front of k_flux, so the copy overlaps the list build and the 2B / 3B kernels
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p, vxx, n * 8, cudaMemcpyHostToDevice, h->vstream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + n, vyy, n * 8, cudaMemcpyHostToDevice, h->vstream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->vel.p + 2 * n, vzz, n * 8, cudaMemcpyHostToDevice, h->vstream));
+        CUDA_TRY(h, cudaEventRecord(h->vel_ev, h->vstream));
     }
     h->uploaded = true;
     return MBPOL_B200_OK;
@@ -884,24 +895,13 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     cudaStream_t s = h->stream;
     const int TB = 128;
     h->launches = 0;
-    // shard of this rank
-    {
-        std::vector<int> bounds(h->nranks + 1);
-        mbpol_b200_shard_bounds(nw, h->nranks, (h->nranks > 1 && h->have_weight) ? h->host_weight.data() : nullptr, bounds.data());
-        h->w0 = bounds[h->rank];
-        h->nown = bounds[h->rank + 1] - bounds[h->rank];
-    }
-    const int w0 = h->w0, nown = h->nown;
-    const int gb = (nw + TB - 1) / TB, go = (nown + TB - 1) / TB;
+    const int gb = (nw + TB - 1) / TB;
     CUDA_TRY(h, h->mono.reserve(9 * (size_t)nw));
     CUDA_TRY(h, h->monoA.reserve(12 * (size_t)nw));
     CUDA_TRY(h, h->out.reserve(h->out_alloc()));
     CUDA_TRY(h, h->cell_id.reserve(nw)); CUDA_TRY(h, h->sorted.reserve(nw)); CUDA_TRY(h, h->unsorted.reserve(nw));
     CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
-    CUDA_TRY(h, h->nb2.reserve((size_t)std::max(nown, 1) * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)std::max(nown, 1) * NB3_CAP));
-    CUDA_TRY(h, h->n2.reserve(nown + 1)); CUDA_TRY(h, h->n3.reserve(nown + 1)); CUDA_TRY(h, h->flag.reserve(1));
-    CUDA_TRY(h, h->off2.reserve(nown + 1)); CUDA_TRY(h, h->off3.reserve(nown + 1)); CUDA_TRY(h, h->cnt3.reserve(nown + 1));
-    CUDA_TRY(h, h->n2ll.reserve(nown + 1)); CUDA_TRY(h, h->counts.reserve(4));
+    CUDA_TRY(h, h->flag.reserve(1)); CUDA_TRY(h, h->counts.reserve(4));
     CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
 
     CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
@@ -925,6 +925,25 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     k_cell_fill<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->cell_fill.p, h->unsorted.p);
     k_sort_cells<<<gb, TB, 0, s>>>(nw, h->cell_id.p, h->cell_cnt.p, h->unsorted.p, h->sorted.p);
     h->launches += 6;
+    // shard of this rank.  The weights of the previous step (all-reduced, read back at its end) are turned into the water ranges
+    // HERE, while the shard-independent kernels above are running: no host work sits between two steps with the GPU idle.
+    {
+        if (h->weights_pending) {
+            h->host_weight.resize(nw);
+            for (int i = 0; i < nw; ++i) h->host_weight[i] = (int)h->host_weight_d[i];
+            h->weights_pending = false;
+        }
+        std::vector<int> bounds(h->nranks + 1);
+        mbpol_b200_shard_bounds(nw, h->nranks, (h->nranks > 1 && h->have_weight) ? h->host_weight.data() : nullptr, bounds.data());
+        h->w0 = bounds[h->rank];
+        h->nown = bounds[h->rank + 1] - bounds[h->rank];
+    }
+    const int w0 = h->w0, nown = h->nown;
+    const int go = (nown + TB - 1) / TB;
+    CUDA_TRY(h, h->nb2.reserve((size_t)std::max(nown, 1) * NB2_CAP)); CUDA_TRY(h, h->nb3.reserve((size_t)std::max(nown, 1) * NB3_CAP));
+    CUDA_TRY(h, h->n2.reserve(nown + 1)); CUDA_TRY(h, h->n3.reserve(nown + 1));
+    CUDA_TRY(h, h->off2.reserve(nown + 1)); CUDA_TRY(h, h->off3.reserve(nown + 1)); CUDA_TRY(h, h->cnt3.reserve(nown + 1));
+    CUDA_TRY(h, h->n2ll.reserve(nown + 1));
     nvtxRangePushA("mbpol_b200: lists");
     const int gw = (int)(((size_t)std::max(nown, 1) * 32 + TB - 1) / TB);      // one warp per owned water
     if (nown > 0) {
@@ -1017,6 +1036,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     nvtxRangePop();
     NvtxRange tail_range("mbpol_b200: flux + reduction + read-back");
     if (h->have_vel) {
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->vel_ev, 0));
         k_flux<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(O, h->vel.p, h->vel.p + n, h->vel.p + 2 * n, h->flags);
         ++h->launches;
     }
@@ -1024,8 +1044,10 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     // ---- reduction over the ranks (NCCL over NVLink, on this stream): forces, per-atom arrays, scalars, weights -------------
     if (h->reduce_mode && h->comm) {
         if (h->reduce_mode == 2) {
+            NCCL_TRY(h, nccl_api().GroupStart());      // one fused launch for the two collectives
             NCCL_TRY(h, nccl_api().ReduceScatter(h->out.p, h->out.p + (size_t)h->rank * h->chunk(), h->chunk(), ncclDouble, ncclSum, h->comm, s));
             NCCL_TRY(h, nccl_api().AllReduce(O.scal, O.scal, (size_t)NSCAL * h->nbeads + nw, ncclDouble, ncclSum, h->comm, s));      // scalars + weights
+            NCCL_TRY(h, nccl_api().GroupEnd());
         } else {
             NCCL_TRY(h, nccl_api().AllReduce(h->out.p, h->out.p, h->out_count() + nw, ncclDouble, ncclSum, h->comm, s));
         }
@@ -1052,10 +1074,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     // box totals: the counts rode through the reduction in the scalar block (bead 0); without one, the shard is all this rank knows
     h->nd_total = (long long)(h->back->tail[0] + 0.5); h->nt_total = (long long)(h->back->tail[1] + 0.5);
     h->have_weight = h->nranks > 1 && h->reduce_mode && h->comm;      // without a communicator the weights of the other ranks are unknown
-    if (h->have_weight) {
-        h->host_weight.resize(nw);
-        for (int i = 0; i < nw; ++i) h->host_weight[i] = (int)h->host_weight_d[i];
-    }
+    h->weights_pending = h->have_weight;      // converted at the start of the next step, under its first kernels
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);
@@ -1120,14 +1139,22 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         h->dl_ev.push_back(e);
     }
     size_t total = 0;
-    for (size_t k = 0; k < jobs.size(); ++k) {
-        CUDA_TRY(h, cudaMemcpyAsync(P + jobs[k].off, h->out.p + jobs[k].off, jobs[k].len * 8, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaEventRecord(h->dl_ev[k], h->stream));
-        total += jobs[k].len;
-    }
+    for (const Job& j : jobs) total += j.len;
     const size_t so = h->scal_offset();
-    CUDA_TRY(h, cudaMemcpyAsync(P + so, h->out.p + so, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
+    const bool one_copy = !jobs.empty() && total < (1u << 20);      // a small slice (multi-GPU): one copy, one wait -- latency, not bandwidth, is what counts
+    if (one_copy) {
+        const size_t a = jobs.front().off, b = jobs.back().off + jobs.back().len;
+        CUDA_TRY(h, cudaMemcpyAsync(P + a, h->out.p + a, (b - a) * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(P + so, h->out.p + so, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
+        for (size_t k = 0; k <= jobs.size(); ++k) CUDA_TRY(h, cudaEventRecord(h->dl_ev[k], h->stream));
+    } else {
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            CUDA_TRY(h, cudaMemcpyAsync(P + jobs[k].off, h->out.p + jobs[k].off, jobs[k].len * 8, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaEventRecord(h->dl_ev[k], h->stream));
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(P + so, h->out.p + so, (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
+    }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nth = total < (1u << 20) ? 1u : std::min(8u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
     auto work = [&](unsigned t) {
