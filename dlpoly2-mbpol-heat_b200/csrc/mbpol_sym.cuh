@@ -10,6 +10,13 @@
 #include "mbpol_tape.cuh"
 // acc += a * b with the operand order fixed in PTX (tools/gen_sym.py --asmfma 1)
 #define SYM_FMA(acc, a, b) asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b))
+#ifndef SYM_STAGGER_NS
+#define SYM_STAGGER_NS 3000      /* measured on B200: 0 / 500 / 1000 / 2000 / 3000 / 5000 / 10000 / 20000 ns -> k_trimers 15.38 / 15.29 / 15.27 / 15.15 / 15.13 / 15.32 / 15.15 / 17.5 ms */
+#endif
+#ifndef SYM_RESTAGGER_ROWS
+#define SYM_RESTAGGER_ROWS 0
+#define SYM_RESTAGGER_NS 0
+#endif
 #ifndef MBPOL_SYM_HEADER
 #define MBPOL_SYM_HEADER "gen/sym_3b.h"
 #endif
@@ -64,6 +71,12 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
             tape_cp_wait<0>();
         }
         __syncthreads();                                   // chunk k visible to every thread
+#if SYM_STAGGER_NS > 0
+        // The two warps of an SM sub-partition (w and w + 4) walk the same code: in lock step both wait for the same instruction-cache
+        // miss.  Warps 4..7 start every chunk a little later: the leaders take the misses while the followers still have cached
+        // code to run, and the followers find the lines in place.
+        if (threadIdx.x >= TAPE_BS / 2) __nanosleep(SYM_STAGGER_NS);
+#endif
         unsigned cp = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
         const unsigned row1 = c_sym_chunks3b[k + 1][1];
         SYM_ROW_DECL
@@ -71,6 +84,9 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         SYM_ROW_FETCH(c_sym_chunks3b[k][1])
 #pragma unroll 1
         for (unsigned row = c_sym_chunks3b[k][1]; row < row1; ++row) {
+#if SYM_RESTAGGER_ROWS > 0
+            if (threadIdx.x >= TAPE_BS / 2 && (row % SYM_RESTAGGER_ROWS) == SYM_RESTAGGER_ROWS - 1) __nanosleep(SYM_RESTAGGER_NS);
+#endif
             SYM_ROW_PRE
             SYM3B_ROW_SWITCH(shape)
             SYM_ROW_POST

@@ -25,6 +25,9 @@
 #ifndef TAPE_BS
 #define TAPE_BS MBPOL_BS3
 #endif
+#ifndef TAPE_STAGGER_NS
+#define TAPE_STAGGER_NS 1000      /* k_dimers 2.37 -> 2.33 ms */
+#endif
 
 __device__ __forceinline__ double tape_lds(unsigned a)
 {
@@ -159,6 +162,9 @@ __device__ __forceinline__ void tape_eval(const double* __restrict__ tape, doubl
             tape_cp_wait<0>();
         }
         __syncthreads();                                   // chunk k visible to every thread
+#if TAPE_STAGGER_NS > 0
+        if (threadIdx.x >= TAPE_BS / 2) __nanosleep(TAPE_STAGGER_NS);      // de-phase the two warps of a sub-partition (see mbpol_sym.cuh)
+#endif
         unsigned cp = buf0 + (k & 1) * (TAPE_CHUNK_DOUBLES * 8);
         unsigned row = chunks[k][1];
         const unsigned row_last = chunks[k + 1][1] - 1;    // last row of this chunk (prefetch clamp)
