@@ -11,11 +11,10 @@
 // acc += a * b with the operand order fixed in PTX (tools/gen_sym.py --asmfma 1)
 #define SYM_FMA(acc, a, b) asm("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc) : "d"(a), "d"(b))
 #ifndef SYM_STAGGER_NS
-#define SYM_STAGGER_NS 3000      /* measured on B200: 0 / 500 / 1000 / 2000 / 3000 / 5000 / 10000 / 20000 ns -> k_trimers 15.38 / 15.29 / 15.27 / 15.15 / 15.13 / 15.32 / 15.15 / 17.5 ms */
+#define SYM_STAGGER_NS 0         /* extra start delay of warps 4..7 per chunk: without SYM_SPLIT_ORDER 0 / 1000 / 3000 ns -> 15.38 / 15.27 / 15.13 ms; with it 0 is best (15.02 vs 15.31) */
 #endif
-#ifndef SYM_RESTAGGER_ROWS
-#define SYM_RESTAGGER_ROWS 0
-#define SYM_RESTAGGER_NS 0
+#ifndef SYM_SPLIT_ORDER
+#define SYM_SPLIT_ORDER 1
 #endif
 #ifndef MBPOL_SYM_HEADER
 #define MBPOL_SYM_HEADER "gen/sym_3b.h"
@@ -77,19 +76,28 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         // code to run, and the followers find the lines in place.
         if (threadIdx.x >= TAPE_BS / 2) __nanosleep(SYM_STAGGER_NS);
 #endif
-        unsigned cp = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
-        const unsigned row1 = c_sym_chunks3b[k + 1][1];
-        SYM_ROW_DECL
-        SYM_ROW_WORDS(c_sym_chunks3b[k][1])
-        SYM_ROW_FETCH(c_sym_chunks3b[k][1])
-#pragma unroll 1
-        for (unsigned row = c_sym_chunks3b[k][1]; row < row1; ++row) {
-#if SYM_RESTAGGER_ROWS > 0
-            if (threadIdx.x >= TAPE_BS / 2 && (row % SYM_RESTAGGER_ROWS) == SYM_RESTAGGER_ROWS - 1) __nanosleep(SYM_RESTAGGER_NS);
+        const unsigned cbase = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
+        const unsigned row0 = c_sym_chunks3b[k][1], row1 = c_sym_chunks3b[k + 1][1];
+        // The rows of a chunk are independent, so every warp may walk them in its own cyclic order: warps 4..7 start in the middle
+        // of the chunk (SYM_SPLIT_ORDER).  The two warps of an SM sub-partition then run different code most of the time and
+        // miss the instruction cache at different moments -- and each finds the half the other one walked first already fetched.
+        unsigned row = row0;
+#if SYM_SPLIT_ORDER
+        if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 2;
 #endif
+        unsigned row_next = row + 1 == row1 ? row0 : row + 1;
+        unsigned cp;
+        SYM_ROW_DECL
+        SYM_ROW_WORDS(row)
+        SYM_ROW_FETCH(row, row_next)
+#pragma unroll 1
+        for (unsigned it = row0; it < row1; ++it) {
+            const unsigned row_next2 = row_next + 1 == row1 ? row0 : row_next + 1;
             SYM_ROW_PRE
             SYM3B_ROW_SWITCH(shape)
             SYM_ROW_POST
+            row = row_next;
+            row_next = row_next2;
         }
         __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }

@@ -185,7 +185,7 @@ static inline void tape_sts(unsigned a, double v) { std::memcpy(SM + a, &v, 8); 
 #define TAPE_COL 8
 using std::fma;
 #include "sym_3b.h"
-extern "C" double sym_host_eval(const double* a, const double* xin, double* gout)
+extern "C" double sym_host_eval(const double* a, const double* xin, double* gout, int split)
 {
     const unsigned* rowvars = SYM3B_ROWVARS_HOST;
     const unsigned xs_t = 64, gs_delta = 37 * 8, buf0 = 4096;
@@ -196,16 +196,22 @@ extern "C" double sym_host_eval(const double* a, const double* xin, double* gout
     for (int i = 0; i < SYM3B_NTAPE; ++i)
         tape_sts(buf0 + 8 * i, SYM3B_COEFIDX_HOST[i] < 0 ? 0.0 : a[SYM3B_COEFIDX_HOST[i]] * (double)SYM3B_COEFNUM_HOST[i] / (double)SYM3B_K);
     double e = 0.0;
-    for (int k = 0; k < SYM3B_NCHUNKS; ++k) {
-        unsigned cp = buf0 + 8 * SYM3B_CHUNKS_HOST[k][2];
-        const unsigned row1 = SYM3B_CHUNKS_HOST[k + 1][1];
+    for (int k = 0; k < SYM3B_NCHUNKS; ++k) {      // the row loop of csrc/mbpol_sym.cuh; `split`: the cyclic order of warps 4..7
+        const unsigned cbase = buf0 + 8 * SYM3B_CHUNKS_HOST[k][2];
+        const unsigned row0 = SYM3B_CHUNKS_HOST[k][1], row1 = SYM3B_CHUNKS_HOST[k + 1][1];
+        unsigned row = row0 + (split ? (row1 - row0) / 2 : 0);
+        unsigned row_next = row + 1 == row1 ? row0 : row + 1;
+        unsigned cp;
         SYM_ROW_DECL
-        SYM_ROW_WORDS(SYM3B_CHUNKS_HOST[k][1])
-        SYM_ROW_FETCH(SYM3B_CHUNKS_HOST[k][1])
-        for (unsigned row = SYM3B_CHUNKS_HOST[k][1]; row < row1; ++row) {
+        SYM_ROW_WORDS(row)
+        SYM_ROW_FETCH(row, row_next)
+        for (unsigned it = row0; it < row1; ++it) {
+            const unsigned row_next2 = row_next + 1 == row1 ? row0 : row_next + 1;
             SYM_ROW_PRE
             SYM3B_ROW_SWITCH(shape)
             SYM_ROW_POST
+            row = row_next;
+            row_next = row_next2;
         }
     }
     SYM_PAIR_FINI
@@ -227,13 +233,14 @@ def test_generated_sym_header_on_the_host(tmp_path, oracle, env):
     subprocess.check_call(["g++", "-O0", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(tmp_path), "-o", str(so), str(tmp_path / "h.cpp")])
     lib = C.CDLL(str(so))
     lib.sym_host_eval.restype = C.c_double
-    lib.sym_host_eval.argtypes = [C.c_void_p] * 3
+    lib.sym_host_eval.argtypes = [C.c_void_p] * 3 + [C.c_int]
     a = np.ascontiguousarray(oracle.coef("3b"))
     rng = np.random.default_rng(17)
     for _ in range(3):
         x = rng.uniform(0.1, 1.2, size=36)
         g = np.zeros(36)
-        E = lib.sym_host_eval(a.ctypes.data, x.ctypes.data, g.ctypes.data)
         Er, gr = oracle.poly("3b", a, x)
-        assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
-        assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()
+        for split in (0, 1):
+            E = lib.sym_host_eval(a.ctypes.data, x.ctypes.data, g.ctypes.data, split)
+            assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
+            assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()

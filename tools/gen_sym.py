@@ -222,7 +222,7 @@ def slots_of(shape):
 
 def emit(rows, shapes, vps, ahead, nsum):
     K = len(vps)
-    tape, rowvars = [], []
+    tape, rowvars, rowmeta = [], [], []
     for (s, key, children) in rows:
         start = len(tape)
         for us, own, leaves in children:
@@ -233,8 +233,8 @@ def emit(rows, shapes, vps, ahead, nsum):
         assert len(tape) - start == slots_of(shapes[s])
         cols = [c for wv in key for c in wv]
         alias = 1 if len(set(cols)) < len(cols) else 0      # some dynamic column is updated twice by this super row: the epilogue must not batch its loads
-        rowvars.extend(w | (v << 8) | (s << 16) | (alias << 31) for (w, v) in key)      # row words: dynamic variables of every image + shape (+ alias flag)
-    segs, chunks = [], []
+        rowmeta.append((s, alias, key))
+    segs, chunks, rowoff = [], [], []
     used, pos, cur = CHUNK + 1, 0, None
     for i, (s, key, children) in enumerate(rows):
         n = slots_of(shapes[s])
@@ -242,6 +242,7 @@ def emit(rows, shapes, vps, ahead, nsum):
         if used + n > CHUNK:
             chunks.append((len(segs), i, pos))
             used, cur = 0, None
+        rowoff.append(8 * used)
         if cur != s:
             segs.append(s)
             cur = s
@@ -249,6 +250,11 @@ def emit(rows, shapes, vps, ahead, nsum):
         used += n
         pos += n
     chunks.append((len(segs), len(rows), len(tape)))
+    # row words: w | v << 6 | shape << 12 | alias << 19 | (byte offset of the row's tape slots inside its chunk / 16) << 20
+    assert len(shapes) <= 128 and NV + 1 + len(PAIRS) <= 64 and CHUNK * 8 // 16 <= 1024
+    for (sid, alias, key), off in zip(rowmeta, rowoff):
+        assert off % 16 == 0
+        rowvars.extend(w | (v << 6) | (sid << 12) | (alias << 19) | ((off // 16) << 20) for (w, v) in key)
     nfp = 0
     body_of = {}
     jj = range(K)
@@ -330,6 +336,7 @@ def emit(rows, shapes, vps, ahead, nsum):
     L.append("static const unsigned char SYM%s_COEFNUM_HOST[%d] = {%s};" % (Tg, len(tape), ",".join(str(n) for c, n in tape)))
     L.append("static const int SYM%s_CHUNKS_HOST[%d][3] = {%s};" % (Tg, len(chunks), ",".join("{%d,%d,%d}" % c for c in chunks)))
     L.append("#define SYM_ROWVARS_SPARE %d" % (K * (1 + WORDS_AHEAD)))
+
     if PAIRS:
         L.append("#define SYM_PAIR_INIT double xq[%d] = {%s}, gq[%d] = {%s};" % (len(PAIRS), ", ".join("x[%d] + x[%d]" % p for p in PAIRS), len(PAIRS), ", ".join("0.0" for p in PAIRS)))
         L.append("#define SYM_PAIR_FINI %s" % " ".join("g[%d] += gq[%d]; g[%d] += gq[%d];" % (p[0], i, p[1], i) for i, p in enumerate(PAIRS)))
@@ -340,27 +347,27 @@ def emit(rows, shapes, vps, ahead, nsum):
     # variables) is fetched while this row's body runs; with WORDS_AHEAD the row words themselves are read one row earlier
     # still, so that the constant-memory latency is off the address computation.
     jj = range(K)
-    L.append("#define SYM_ROW_DECL unsigned nshape, nalias, %s; double %s;%s" % (
+    L.append("#define SYM_ROW_DECL unsigned nshape, nalias, noff, %s; double %s;%s" % (
         ", ".join("nw_%d, nv_%d" % (j, j) for j in jj), ", ".join("nxw_%d, nxv_%d" % (j, j) for j in jj),
         (" unsigned %s;" % ", ".join("rw_%d" % j for j in jj)) if WORDS_AHEAD else ""))
     unpack = " ".join(
-        "{ %snw_%d = xs_t + (vw_%d & 255u) * TAPE_COL; nv_%d = xs_t + ((vw_%d >> 8) & 255u) * TAPE_COL; nxw_%d = tape_lds(nw_%d); nxv_%d = tape_lds(nv_%d); }"
-        % ("nshape = (vw_%d >> 16) & 0x7fffu; nalias = vw_%d >> 31; " % (j, j) if j == 0 else "", j, j, j, j, j, j, j, j) for j in jj)
+        "{ %snw_%d = xs_t + (vw_%d & 63u) * TAPE_COL; nv_%d = xs_t + ((vw_%d >> 6) & 63u) * TAPE_COL; nxw_%d = tape_lds(nw_%d); nxv_%d = tape_lds(nv_%d); }"
+        % ("nshape = (vw_%d >> 12) & 127u; nalias = (vw_%d >> 19) & 1u; noff = (vw_%d >> 20) << 4; " % (j, j, j) if j == 0 else "", j, j, j, j, j, j, j, j) for j in jj)
     if WORDS_AHEAD:
         L.append("#define SYM_ROW_WORDS(ROWIDX) { %s }" % " ".join("rw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj))
-        L.append("#define SYM_ROW_FETCH(ROWIDX) { %s %s SYM_ROW_WORDS((ROWIDX) + 1) }" % (" ".join("const unsigned vw_%d = rw_%d;" % (j, j) for j in jj), unpack))
+        L.append("#define SYM_ROW_FETCH(ROWIDX, ROWAFTER) { %s %s SYM_ROW_WORDS(ROWAFTER) }" % (" ".join("const unsigned vw_%d = rw_%d;" % (j, j) for j in jj), unpack))
     else:
         L.append("#define SYM_ROW_WORDS(ROWIDX)")
-        L.append("#define SYM_ROW_FETCH(ROWIDX) { %s %s }" % (" ".join("const unsigned vw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj), unpack))
+        L.append("#define SYM_ROW_FETCH(ROWIDX, ROWAFTER) { %s %s }" % (" ".join("const unsigned vw_%d = rowvars[(ROWIDX) * %d + %d];" % (j, K, j) for j in jj), unpack))
     if POST == "inbody":
         # the epilogue lives in the shape bodies; the header of the next row is fetched AFTER the body (its x loads fly during the
         # dispatch of the next row), straight into the registers the next row reads: no double-buffered header, no register moves
-        L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s" % " ".join(
+        L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; cp = cbase + noff; %s" % " ".join(
             "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
             % (j, j, j, j, j, j, j, j, j, j, j, j) for j in jj))
-        L.append("#define SYM_ROW_POST SYM_ROW_FETCH(row + 1)")
+        L.append("#define SYM_ROW_POST SYM_ROW_FETCH(row_next, row_next2)")
     else:
-      L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; %s SYM_ROW_FETCH(row + 1)" % " ".join(
+      L.append("#define SYM_ROW_PRE const unsigned shape = nshape; const bool alias = nalias != 0u; cp = cbase + noff; %s SYM_ROW_FETCH(row_next, row_next2)" % " ".join(
         "const unsigned aw_%d = nw_%d, av_%d = nv_%d; const double xw_%d = nxw_%d, xv_%d = nxv_%d; const double p2_%d = xv_%d * xw_%d; double Tw_%d = 0.0;"
         % (j, j, j, j, j, j, j, j, j, j, j, j) for j in jj))
     if POST == "inbody":
