@@ -82,8 +82,12 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         // of the chunk (SYM_SPLIT_ORDER).  The two warps of an SM sub-partition then run different code most of the time and
         // miss the instruction cache at different moments -- and each finds the half the other one walked first already fetched.
         unsigned row = row0;
-#if SYM_SPLIT_ORDER
+#if SYM_SPLIT_ORDER == 1
         if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 2;
+#elif SYM_SPLIT_ORDER == 8
+        row += ((threadIdx.x >> 5) * (row1 - row0)) / (TAPE_BS / 32);
+#elif SYM_SPLIT_ORDER == 4
+        row += (((threadIdx.x >> 5) & 3) * (row1 - row0)) / 8 + (threadIdx.x >= TAPE_BS / 2 ? (row1 - row0) / 2 : 0);
 #endif
         unsigned row_next = row + 1 == row1 ? row0 : row + 1;
         unsigned cp;

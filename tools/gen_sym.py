@@ -34,10 +34,13 @@ DISPATCH = os.environ.get("SYM_DISPATCH", "if")
 ASMFMA = int(os.environ.get("SYM_ASMFMA", "0"))
 POST = os.environ.get("SYM_POST", "inbody")       # row epilogue: "serial" (round-2 first form) | "batch" (all gradient-column loads first) | "inbody" (batch, inside the shape bodies)
 WORDS_AHEAD = int(os.environ.get("SYM_WORDS_AHEAD", "1"))   # row words are read from constant memory this many rows before they are unpacked
-# trie order and representative rule found by tools/search_sym_order.py for K = z (J = FP64 instructions + 0.28 * leaf pairs of code):
-# 73 920 instructions per trimer, 138 super rows of 52 shapes, 9 495 leaf pairs of code (orbit order reversed: 79 791 / 207 / 61 / 9 408)
-DEFAULT_ORDER = "1,2,0,11,8,7,10,9,4,5,6,3"
-DEFAULT_REPSEL = "min"
+# trie order and representative rule found by tools/search_sym_order.py for K = z (objective: FP64 instructions + 0.6 * leaf pairs of
+# code, pair sums included): 71 589 instructions per trimer, 120 super rows of 47 shapes, 11 079 leaf pairs of code -- measured
+# 14.75 ms; "1,2,0,11,8,7,10,9,4,5,6,3" / min (72 414 / 138 / 52 / 9 204): 14.97 ms; the reversed orbit order of the first version
+# (79 791 / 207 / 61 / 9 408): 17.4 ms.  Orders must be MEASURED: "0,11,10,9,8,7,1,2,6,5,3,4" / min (77 556 instructions, only 6 744
+# leaf pairs of code) runs at 16.2 ms in lock step and at 32.8 ms with SYM_SPLIT_ORDER (experiments/README.md section 9).
+DEFAULT_ORDER = "1,2,0,10,9,8,7,5,11,6,4,3"
+DEFAULT_REPSEL = "max"
 NV = 36
 UNIT = NV
 # atoms: 0 Oa 1 Ha1 2 Ha2 3 Ob 4 Hb1 5 Hb2 6 Oc 7 Hc1 8 Hc2 ; variable n = distance (V3A[n], V3B[n]) (csrc/mbpol_device.cuh)
