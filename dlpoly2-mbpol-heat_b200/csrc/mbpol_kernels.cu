@@ -1156,7 +1156,7 @@ int mbpol_b200_download(mbpol_b200_handle* h, double* fxx, double* fyy, double* 
         CUDA_TRY(h, cudaEventRecord(h->dl_ev[jobs.size()], h->stream));
     }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nth = total < (1u << 20) ? 1u : std::min(8u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
+    const unsigned nth = total < (1u << 20) ? 1u : std::min(16u, std::max(1u, hw / (unsigned)std::max(1, h->nranks)));
     auto work = [&](unsigned t) {
         cudaSetDevice(h->device);
         for (size_t k = 0; k < jobs.size(); ++k) {
