@@ -353,6 +353,12 @@ __global__ void k_flux(OutPtrs O, const double* __restrict__ vx, const double* _
 // ---------------------------------------------------------------------------------------------------------
 // FP64 roofline probe: 8 independent register-resident DFMA chains per thread (the denominator bench.py quotes)
 // ---------------------------------------------------------------------------------------------------------
+// out[i] += acc[i]: the caller's "+=" done on the device (fused end of mbpol_b200_forces)
+__global__ void k_accumulate(size_t n, const double* __restrict__ acc, double* __restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] += acc[i];
+}
+
 __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b)
 {
     double acc[8];
@@ -575,6 +581,13 @@ struct mbpol_b200_handle {
     double* host_weight_d = nullptr;           // pinned: per-water load-balancing weights of the previous step (all ranks)
     std::vector<int> host_weight;
     bool have_weight = false, weights_pending = false;
+    // fused end of mbpol_b200_forces (caller arrays in pinned memory): the caller's current values travel up on vstream while the
+    // step runs, the device adds them (k_accumulate) and the sums go straight back into the caller's arrays -- no host "+=" pass
+    struct FusedJob { double* dst; size_t off, len; };
+    std::vector<FusedJob> fused;
+    DevBuf<double> acc;
+    unsigned acc_mask = ~0u;      // which per-atom arrays the zero-filled parts of acc were prepared for
+    cudaEvent_t acc_ev = nullptr;
     ncclComm_t comm = nullptr;
     int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
@@ -727,7 +740,8 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     if (cudaStreamCreateWithFlags(&h->vstream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->vel_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+        cudaEventCreateWithFlags(&h->vel_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->acc_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     if (cudaMallocHost(&h->back, sizeof(*h->back)) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     *handle = h;
@@ -748,6 +762,7 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     cudaStreamDestroy(h->stream);
     if (h->vstream) cudaStreamDestroy(h->vstream);
     if (h->vel_ev) cudaEventDestroy(h->vel_ev);
+    if (h->acc_ev) cudaEventDestroy(h->acc_ev);
     delete h;
     return MBPOL_B200_OK;
 }
@@ -1054,6 +1069,14 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         h->launches += 2;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[4], s));
+    if (!h->fused.empty()) {      // fused end of mbpol_b200_forces: caller values (already on the device) + this step, straight into the caller's arrays
+        const size_t a = h->fused.front().off, b = h->fused.back().off + h->fused.back().len;
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->acc_ev, 0));
+        k_accumulate<<<(unsigned)std::min<size_t>((b - a + 255) / 256, 148 * 8), 256, 0, s>>>(b - a, h->acc.p + a, h->out.p + a);
+        ++h->launches;
+        for (const auto& j : h->fused) CUDA_TRY(h, cudaMemcpyAsync(j.dst, h->out.p + j.off, j.len * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(h->pinned + h->scal_offset(), h->out.p + h->scal_offset(), (size_t)NSCAL * h->nbeads * 8, cudaMemcpyDeviceToHost, s));
+    }
     // ---- the one read-back of the step: counts, overflow flag, weights ---------------------------------------------------
     CUDA_TRY(h, cudaMemcpyAsync(h->back->counts, h->counts.p, 32, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemcpyAsync(&h->back->flag, h->flag.p, 4, cudaMemcpyDeviceToHost, s));
@@ -1219,10 +1242,72 @@ int mbpol_b200_forces(mbpol_b200_handle* h, int imcon, const double* cell, int n
     auto ms_since = [](clk::time_point t) { return std::chrono::duration<float, std::milli>(clk::now() - t).count(); };
     clk::time_point t0 = clk::now();
     if (int rc = mbpol_b200_upload(h, imcon, cell, nttm2, listttm2, mxatms, xxx, yyy, zzz, vxx, vyy, vzz)) return rc;
+    // Caller arrays in pinned (page-locked) memory: fused end.  Their current values go up on the side stream now, the device adds
+    // them after the reduction and copies the sums back inside the step -- the reference's "+=" without a host pass over 23 MB.
+    h->fused.clear();
+    {
+        double* arr[6] = {fxx, fyy, fzz, atomic_energy, atomic_stress, atomic_fdecomp};
+        const size_t n = h->mxatms;
+        const size_t a0[6] = {0, n, 2 * n, 3 * n, 4 * n, 13 * n}, a1[6] = {n, 2 * n, 3 * n, 4 * n, 13 * n, 22 * n};
+        bool pinned = fxx && fyy && fzz && !std::getenv("MBPOL_B200_NO_FUSED_DOWNLOAD");
+        unsigned mask = 0;
+        for (int k = 0; k < 6 && pinned; ++k)
+            if (arr[k]) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, arr[k]) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); pinned = false; }
+                mask |= 1u << k;
+            }
+        if (pinned) {
+            const bool slice = h->reduce_mode == 2 && h->comm && h->nranks > 1;
+            const size_t lo = slice ? std::min((size_t)h->rank * h->chunk(), h->atom_count()) : 0;
+            const size_t hi = slice ? std::min((size_t)(h->rank + 1) * h->chunk(), h->atom_count()) : h->atom_count();
+            CUDA_TRY(h, h->acc.reserve(h->out_alloc()));
+            if (h->pinned_cap < h->out_count()) {
+                if (h->pinned) cudaFreeHost(h->pinned);
+                h->pinned = nullptr; h->pinned_cap = 0;
+                CUDA_TRY(h, cudaMallocHost(&h->pinned, h->out_count() * 8));
+                h->pinned_cap = h->out_count();
+            }
+            if (h->acc_mask != mask) {      // arrays that are not requested stay zero in acc
+                CUDA_TRY(h, cudaMemsetAsync(h->acc.p, 0, h->atom_count() * 8, h->vstream));
+                h->acc_mask = mask;
+            }
+            for (int k = 0; k < 6; ++k) {
+                if (!arr[k]) continue;
+                const size_t x = std::max(a0[k], lo), y = std::min(a1[k], hi);
+                if (x >= y) continue;
+                h->fused.push_back({arr[k] + (x - a0[k]), x, y - x});
+                CUDA_TRY(h, cudaMemcpyAsync(h->acc.p + x, arr[k] + (x - a0[k]), (y - x) * 8, cudaMemcpyHostToDevice, h->vstream));
+            }
+            CUDA_TRY(h, cudaEventRecord(h->acc_ev, h->vstream));
+        }
+    }
     h->ms[8] = ms_since(t0); t0 = clk::now();
-    if (int rc = mbpol_b200_compute(h)) return rc;
+    const int rcc = mbpol_b200_compute(h);
+    const bool fused = !h->fused.empty();
+    h->fused.clear();
+    if (rcc) return rcc;
     h->ms[9] = ms_since(t0); t0 = clk::now();
-    const int rc = mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+    int rc = MBPOL_B200_OK;
+    if (fused) {      // the per-atom arrays are already home; the scalars wait in the pinned block
+        const double* P = h->pinned;
+        const size_t so = h->scal_offset();
+        const bool reduced = h->reduce_mode && h->comm && h->nranks > 1;
+        for (int b = 0; b < h->nbeads; ++b) {
+            const double* sc = P + so + (size_t)b * NSCAL;
+            const bool mine = !reduced || h->rank == 0;
+            if (mine) {
+                if (eng2) eng2[b] += sc[S_ENG2];
+                if (vir2) vir2[b] += sc[S_VIR2];
+                if (eng3) eng3[b] += sc[S_ENG3];
+                if (vir3) vir3[b] += sc[S_VIR3];
+                if (stress) for (int q = 0; q < 9; ++q) stress[9 * b + q] += sc[S_STRESS + q];
+            }
+            if (jflux) for (int q = 0; q < 9; ++q) jflux[9 * b + q] = mine ? sc[S_JFLUX + q] : 0.0;
+        }
+    } else {
+        rc = mbpol_b200_download(h, fxx, fyy, fzz, eng2, vir2, eng3, vir3, stress, atomic_energy, atomic_stress, atomic_fdecomp, jflux);
+    }
     h->ms[10] = ms_since(t0);
     return rc;
 }

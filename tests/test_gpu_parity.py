@@ -124,6 +124,35 @@ def test_accumulate_semantics(mb, box64):
     assert abs(r["engsrp"] - 10.0 - (a["eng2"] + a["eng3"])) < 1e-9 * abs(a["eng2"])
 
 
+def test_accumulate_semantics_pinned_arrays(mb, box64):
+    """Caller arrays in page-locked memory take the fused end of mbpol_b200_forces (values uploaded, added on the device, copied
+    straight back): same "+=" semantics, for every per-atom array, also when the call is repeated on the same arrays."""
+    h = mb.mbpol_init(box64["nttm2"], flags=7)
+    a = mb.run_box(h, box64, want_stress=True)
+    n = box64["mxatms"]
+    arrs = {"fxx": np.full(n, 1.5), "fyy": np.full(n, -2.0), "fzz": np.zeros(n), "ae": np.full(n, 0.25), "as": np.full(9 * n, -1.0), "afd": np.full(9 * n, 3.0)}
+    for v in arrs.values():
+        mb.host_register(v)
+    try:
+        for rep in (1, 2):
+            st = np.arange(9.0)
+            r = mb.mbpol_forces(h, box64["imcon"], box64["cell"], box64["nttm2"], box64["listttm2"], box64["xxx"], box64["yyy"], box64["zzz"],
+                                arrs["fxx"], arrs["fyy"], arrs["fzz"], engsrp=10.0, stress=st, atomic_energy=arrs["ae"], atomic_stress=arrs["as"],
+                                atomic_fdecomp=arrs["afd"], vxx=box64["vxx"], vyy=box64["vyy"], vzz=box64["vzz"])
+            assert rel_rms(arrs["fxx"] - 1.5, rep * a["fxx"]) < 1e-11 and rel_rms(arrs["fyy"] + 2.0, rep * a["fyy"]) < 1e-11
+            assert rel_rms(arrs["fzz"], rep * a["fzz"]) < 1e-11
+            assert rel_rms(arrs["ae"] - 0.25, rep * a["atomic_energy"]) < 1e-11
+            assert rel_rms(arrs["as"] + 1.0, rep * a["atomic_stress"]) < 1e-11
+            assert rel_rms(arrs["afd"] - 3.0, rep * a["atomic_fdecomp"]) < 1e-11
+            assert rel_rms(st - np.arange(9.0), a["stress"]) < 1e-11
+            assert abs(r["engsrp"] - 10.0 - (a["eng2"] + a["eng3"])) < 1e-9 * abs(a["eng2"])
+            assert rel_rms(r["jflux"], a["jflux"]) < 1e-10
+    finally:
+        for v in arrs.values():
+            mb.host_unregister(v)
+        mb.mbpol_fini(h)
+
+
 def test_cell_types(mb, synth):
     """imcon 1/2/3 (mbpol.f90:1319-1358) on the same cubic cell give the same lists and energies; imcon 0 is rejected."""
     box = synth.make_water_box(216, seed=3)
