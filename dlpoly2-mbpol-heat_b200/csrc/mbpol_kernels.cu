@@ -591,6 +591,7 @@ struct mbpol_b200_handle {
     ncclComm_t comm = nullptr;
     int reduce_mode = 0;                       // 0 none, 1 all-reduce, 2 reduce-scatter of the per-atom part (scalars: all-reduce)
     long long nd_total = 0, nt_total = 0, nd_shard = 0, nt_shard = 0, launches = 0;
+    bool ms_stale = false;
     float ms[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // 0..7: device phases (events), 8..10: host wall time of upload / compute / download in the last mbpol_b200_forces
     // packed output buffer: [22 per-atom arrays of mxatms | pad to nranks equal chunks | NSCAL scalars per bead]
     size_t atom_count() const { return (size_t)22 * mxatms; }
@@ -1098,6 +1099,15 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     h->nd_total = (long long)(h->back->tail[0] + 0.5); h->nt_total = (long long)(h->back->tail[1] + 0.5);
     h->have_weight = h->nranks > 1 && h->reduce_mode && h->comm;      // without a communicator the weights of the other ranks are unknown
     h->weights_pending = h->have_weight;      // converted at the start of the next step, under its first kernels
+    h->ms_stale = true;      // the phase times are read from the events only when somebody asks (refresh_phase_times)
+    return MBPOL_B200_OK;
+}
+
+static void refresh_phase_times(mbpol_b200_handle* h)
+{
+    if (!h->ms_stale) return;
+    h->ms_stale = false;
+    if (h->nw == 0) return;
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);
@@ -1106,7 +1116,6 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     cudaEventElapsedTime(&h->ms[5], h->ev[6], h->ev[7]);      // k_trimers_gather
     cudaEventElapsedTime(&h->ms[6], h->ev[8], h->ev[4]);      // reduction
     cudaEventElapsedTime(&h->ms[7], h->ev[2], h->ev[5]);      // incidence lists
-    return MBPOL_B200_OK;
 }
 
 int mbpol_b200_compute(mbpol_b200_handle* h)
@@ -1354,6 +1363,7 @@ int mbpol_b200_get_lists(mbpol_b200_handle* h, int* dimers, long long dimer_cap,
 int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches)
 {
     if (!h) return MBPOL_B200_EINVAL;
+    refresh_phase_times(h);
     if (ms) std::copy(h->ms, h->ms + 4, ms);
     if (launches) *launches = h->launches;
     return MBPOL_B200_OK;
@@ -1362,6 +1372,7 @@ int mbpol_b200_kernel_times(mbpol_b200_handle* h, float* ms, long long* launches
 int mbpol_b200_phase_times(mbpol_b200_handle* h, float* ms, int n)
 {
     if (!h || !ms || n < 0) return MBPOL_B200_EINVAL;
+    refresh_phase_times(h);
     for (int k = 0; k < n; ++k) ms[k] = k < 11 ? h->ms[k] : 0.f;
     return MBPOL_B200_OK;
 }
