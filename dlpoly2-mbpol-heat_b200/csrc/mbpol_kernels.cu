@@ -557,18 +557,18 @@ struct mbpol_b200_handle {
     int mxatms = 0, imcon = 0;
     bool have_vel = false, uploaded = false;
     std::string err;
-    cudaStream_t stream = nullptr, vstream = nullptr;      // vstream: velocity upload (needed only by k_flux at the end of the step)
+    cudaStream_t stream = nullptr, vstream = nullptr, s2b = nullptr;      // s2b: the 2B chain of a step, concurrent with the 3B chain on `stream`      // vstream: velocity upload (needed only by k_flux at the end of the step)
     cudaEvent_t vel_ev = nullptr;
     cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CellInfo C;
     Grid G;
     int ncells = 0;
     DevBuf<double> xyz, vel, mono, monoA, out, rec, rec2;         // rec: one 40-double record per trimer of the shard (k_trimers -> k_trimers_gather)
-    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, unsorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur;
+    DevBuf<int> list, cell_id, cell_cnt, cell_fill, sorted, unsorted, nb2, n2, nb3, n3, trimers, flag, inc_off, inc_cur, inc_off2, inc_cur2;
     DevBuf<unsigned> inc, inc2;                            // incidence lists water -> (trimer << 2 | slot) of the shard
     DevBuf<int2> dimers;
     DevBuf<long long> off2, off3, cnt3, n2ll, counts;
-    DevBuf<char> scan_tmp;
+    DevBuf<char> scan_tmp, scan_tmp2;
     std::vector<int> host_list, list_cache;     // list_cache: the caller's listttm2 of the last upload
     int list_mxb = -1;
     double* pinned = nullptr;
@@ -625,12 +625,14 @@ int scan_ll(mbpol_b200_handle* h, const long long* in, long long* out, int n)
     CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, bytes, in, out, n, h->stream));
     return 0;
 }
-int scan_int(mbpol_b200_handle* h, const int* in, int* out, int n)
+int scan_int(mbpol_b200_handle* h, const int* in, int* out, int n, bool second_stream = false)
 {
     size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream);
-    CUDA_TRY(h, h->scan_tmp.reserve(bytes));
-    CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp.p, bytes, in, out, n, h->stream));
+    cudaStream_t s = second_stream ? h->s2b : h->stream;
+    auto& tmp = second_stream ? h->scan_tmp2 : h->scan_tmp;      // the two chains of a step scan concurrently
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, s);
+    CUDA_TRY(h, tmp.reserve(bytes));
+    CUDA_TRY(h, cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, s));
     return 0;
 }
 
@@ -740,6 +742,11 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
         }
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    {
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        if (cudaStreamCreateWithPriority(&h->s2b, cudaStreamNonBlocking, hi_pri) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    }
     if (cudaStreamCreateWithFlags(&h->vstream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->vel_ev, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->acc_ev, cudaEventDisableTiming) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
@@ -762,6 +769,7 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     for (cudaEvent_t e : h->dl_ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
     if (h->vstream) cudaStreamDestroy(h->vstream);
+    if (h->s2b) cudaStreamDestroy(h->s2b);
     if (h->vel_ev) cudaEventDestroy(h->vel_ev);
     if (h->acc_ev) cudaEventDestroy(h->acc_ev);
     delete h;
@@ -919,6 +927,7 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, h->cell_cnt.reserve(h->ncells + 1)); CUDA_TRY(h, h->cell_fill.reserve(h->ncells + 1));
     CUDA_TRY(h, h->flag.reserve(1)); CUDA_TRY(h, h->counts.reserve(4));
     CUDA_TRY(h, h->inc_off.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur.reserve(nw + 1));
+    CUDA_TRY(h, h->inc_off2.reserve(nw + 1)); CUDA_TRY(h, h->inc_cur2.reserve(nw + 1));
 
     CUDA_TRY(h, cudaEventRecord(h->ev[0], s));
     CUDA_TRY(h, cudaMemsetAsync(h->out.p, 0, h->out_alloc() * 8, s));
@@ -1004,31 +1013,39 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
     nvtxRangePop();
 
-    // ---- 2B ---------------------------------------------------------------------------------------------------------
+    // ---- 2B: on its own (high-priority) stream, CONCURRENT with the 3B chain below.  Both polynomial kernels fill whole SMs, so
+    // nothing overlaps inside an SM -- but the CTAs of the two kernels pack the SMs back to back (no partial last wave of k_dimers,
+    // no idle SMs under the small incidence kernels), which is what a rank of an 8-GPU step loses otherwise (7.7 waves of trimers).
+    // The two gathers add into the same per-atom arrays: k_trimers_gather waits for ev[2].
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     nvtxRangePushA("mbpol_b200: 2B");
     if (h->est_nd > 0) {
+        cudaStream_t s2 = h->s2b;
+        CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev[1], 0));
         const unsigned gd = (unsigned)((h->est_nd + MBPOL_BS2 - 1) / MBPOL_BS2);
         const unsigned gi = (unsigned)std::min<long long>((2 * h->est_nd + 255) / 256, 1 << 20);
-        CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
-        CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
-        k_inc_count<2><<<gi, 256, 0, s>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off.p);
-        if (int rc = scan_int(h, h->inc_off.p, h->inc_off.p, nw + 1)) return rc;
-        k_inc_fill<2><<<gi, 256, 0, s>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off.p, h->inc_cur.p, h->inc2.p);
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_off2.p, 0, (size_t)(nw + 1) * 4, s2));
+        CUDA_TRY(h, cudaMemsetAsync(h->inc_cur2.p, 0, (size_t)(nw + 1) * 4, s2));
+        k_inc_count<2><<<gi, 256, 0, s2>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off2.p);
+        if (int rc = scan_int(h, h->inc_off2.p, h->inc_off2.p, nw + 1, true)) return rc;
+        k_inc_fill<2><<<gi, 256, 0, s2>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off2.p, h->inc_cur2.p, h->inc2.p);
         if (h->engine2b == 3)
-            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_fat2b[h->device], h->rec2.p);
+            k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s2>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_fat2b[h->device], h->rec2.p);
         else
-            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_tape2b[h->device], h->rec2.p);
-        k_dimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc2.p, h->dimers.p, h->rec2.p, h->monoA.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
+            k_dimers<1><<<gd, MBPOL_BS2, SMEM2B, s2>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_tape2b[h->device], h->rec2.p);
+        k_dimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s2>>>(nw, h->inc_off2.p, h->inc2.p, h->dimers.p, h->rec2.p, h->monoA.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
         h->launches += 6;
+        CUDA_TRY(h, cudaEventRecord(h->ev[2], s2));
+    } else {
+        CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     }
-    CUDA_TRY(h, cudaEventRecord(h->ev[2], s));
     nvtxRangePop();
     nvtxRangePushA("mbpol_b200: 3B");
     // ---- 3B: incidence lists of the shard (count -> exclusive scan -> fill), records, gather -----------------------------
     if (h->est_nt > 0) {
         const unsigned gt = (unsigned)((h->est_nt + MBPOL_BS3 - 1) / MBPOL_BS3);
         const unsigned gi = (unsigned)std::min<long long>((3 * h->est_nt + 255) / 256, 1 << 20);
+        CUDA_TRY(h, cudaEventRecord(h->ev[9], s));
         CUDA_TRY(h, cudaMemsetAsync(h->inc_off.p, 0, (size_t)(nw + 1) * 4, s));
         CUDA_TRY(h, cudaMemsetAsync(h->inc_cur.p, 0, (size_t)(nw + 1) * 4, s));
         k_inc_count<3><<<gi, 256, 0, s>>>(h->counts.p + 1, h->trimers.p, h->inc_off.p);
@@ -1042,11 +1059,14 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         else
             k_trimers<1><<<gt, MBPOL_BS3, SMEM3B, s>>>(h->counts.p + 1, h->trimers.p, nw, h->mono.p, h->C, g_tape3b[h->device], h->rec.p);
         CUDA_TRY(h, cudaEventRecord(h->ev[6], s));
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev[2], 0));      // the 2B gather has finished with the per-atom arrays
         k_trimers_gather<<<(unsigned)((nw + 3) / 4), 128, 0, s>>>(nw, h->inc_off.p, h->inc.p, h->trimers.p, h->rec.p, h->monoA.p, h->list.p, xr, yr, zr, h->C, O, h->flags);
         CUDA_TRY(h, cudaEventRecord(h->ev[7], s));
         h->launches += 6;
     } else {
+        CUDA_TRY(h, cudaEventRecord(h->ev[9], s));
         for (int k = 5; k < 8; ++k) CUDA_TRY(h, cudaEventRecord(h->ev[k], s));
+        CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev[2], 0));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev[3], s));
     nvtxRangePop();
@@ -1110,12 +1130,12 @@ static void refresh_phase_times(mbpol_b200_handle* h)
     if (h->nw == 0) return;
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&h->ms[2], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->ms[2], h->ev[9], h->ev[3]);      // 3B chain (overlaps the 2B chain: ms[1] + ms[2] > the step)
     cudaEventElapsedTime(&h->ms[3], h->ev[0], h->ev[4]);
     cudaEventElapsedTime(&h->ms[4], h->ev[5], h->ev[6]);      // k_trimers alone (the roofline kernel)
     cudaEventElapsedTime(&h->ms[5], h->ev[6], h->ev[7]);      // k_trimers_gather
     cudaEventElapsedTime(&h->ms[6], h->ev[8], h->ev[4]);      // reduction
-    cudaEventElapsedTime(&h->ms[7], h->ev[2], h->ev[5]);      // incidence lists
+    cudaEventElapsedTime(&h->ms[7], h->ev[9], h->ev[5]);      // incidence lists
 }
 
 int mbpol_b200_compute(mbpol_b200_handle* h)
