@@ -580,7 +580,7 @@ struct mbpol_b200_handle {
     struct HostBack { long long counts[4]; double tail[3]; int flag; int pad; } *back = nullptr;     // pinned: read back once per step
     double* host_weight_d = nullptr;           // pinned: per-water load-balancing weights of the previous step (all ranks)
     std::vector<int> host_weight;
-    bool have_weight = false, weights_pending = false;
+    bool have_weight = false, weights_pending = false, two_streams = false;
     // fused end of mbpol_b200_forces (caller arrays in pinned memory): the caller's current values travel up on vstream while the
     // step runs, the device adds them (k_accumulate) and the sums go straight back into the caller's arrays -- no host "+=" pass
     struct FusedJob { double* dst; size_t off, len; };
@@ -742,6 +742,7 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
         }
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
+    if (const char* e = std::getenv("MBPOL_B200_TWO_STREAMS")) h->two_streams = std::atoi(e) != 0;
     {
         int lo_pri = 0, hi_pri = 0;
         cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
@@ -1013,21 +1014,22 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
     CUDA_TRY(h, cudaEventRecord(h->ev[1], s));
     nvtxRangePop();
 
-    // ---- 2B: on its own (high-priority) stream, CONCURRENT with the 3B chain below.  Both polynomial kernels fill whole SMs, so
-    // nothing overlaps inside an SM -- but the CTAs of the two kernels pack the SMs back to back (no partial last wave of k_dimers,
-    // no idle SMs under the small incidence kernels), which is what a rank of an 8-GPU step loses otherwise (7.7 waves of trimers).
-    // The two gathers add into the same per-atom arrays: k_trimers_gather waits for ev[2].
+    // ---- 2B.  Optionally (MBPOL_B200_TWO_STREAMS=1) on its own high-priority stream, concurrent with the 3B chain below: both
+    // polynomial kernels fill whole SMs, so nothing overlaps inside an SM, but the CTAs of the two kernels pack the SMs back to back.
+    // Measured: one GPU 20.12 -> 20.06 ms, two 10.64 -> 10.56, but four 5.77 -> 5.94 and eight 3.22 -> 3.33 ms per step (the
+    // emulated 1/8 shard on one GPU had gained 0.08 ms): off by default.  The two gathers add into the same per-atom arrays:
+    // k_trimers_gather waits for ev[2].
     const double* xr = h->xyz.p; const double* yr = h->xyz.p + n; const double* zr = h->xyz.p + 2 * n;
     nvtxRangePushA("mbpol_b200: 2B");
     if (h->est_nd > 0) {
-        cudaStream_t s2 = h->s2b;
-        CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev[1], 0));
+        cudaStream_t s2 = h->two_streams ? h->s2b : s;
+        if (h->two_streams) CUDA_TRY(h, cudaStreamWaitEvent(s2, h->ev[1], 0));
         const unsigned gd = (unsigned)((h->est_nd + MBPOL_BS2 - 1) / MBPOL_BS2);
         const unsigned gi = (unsigned)std::min<long long>((2 * h->est_nd + 255) / 256, 1 << 20);
         CUDA_TRY(h, cudaMemsetAsync(h->inc_off2.p, 0, (size_t)(nw + 1) * 4, s2));
         CUDA_TRY(h, cudaMemsetAsync(h->inc_cur2.p, 0, (size_t)(nw + 1) * 4, s2));
         k_inc_count<2><<<gi, 256, 0, s2>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off2.p);
-        if (int rc = scan_int(h, h->inc_off2.p, h->inc_off2.p, nw + 1, true)) return rc;
+        if (int rc = scan_int(h, h->inc_off2.p, h->inc_off2.p, nw + 1, h->two_streams)) return rc;
         k_inc_fill<2><<<gi, 256, 0, s2>>>(h->counts.p, reinterpret_cast<const int*>(h->dimers.p), h->inc_off2.p, h->inc_cur2.p, h->inc2.p);
         if (h->engine2b == 3)
             k_dimers<3><<<gd, MBPOL_BS2, SMEM2B, s2>>>(h->counts.p, h->dimers.p, nw, h->mono.p, h->C, g_fat2b[h->device], h->rec2.p);
