@@ -84,6 +84,8 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         unsigned row = row0;
 #if SYM_SPLIT_ORDER == 1
         if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 2;
+#elif SYM_SPLIT_ORDER == 3
+        if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 3;
 #elif SYM_SPLIT_ORDER == 8
         row += ((threadIdx.x >> 5) * (row1 - row0)) / (TAPE_BS / 32);
 #elif SYM_SPLIT_ORDER == 4
