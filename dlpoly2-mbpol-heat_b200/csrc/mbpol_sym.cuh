@@ -2,10 +2,17 @@
 // polynomial (tools/gen_sym.py has the why and the format).
 //
 // A super row = the K-orbit of a fat row: |K| dynamic (w_j, v_j) pairs (row words, x reads and gradient read-modify-writes
-// in the per-thread shared-memory columns, exactly like engine 3) and ONE static body in which every coefficient of the
-// tape is loaded once and feeds 2|K| DFMAs on |K| independent chains -- image j works on the statically renamed registers
-// x[sigma_j(u)], x[sigma_j(c)], g[...].  Same staging as engines 1 and 3: cp.async double-buffered 16 KB chunks, broadcast
-// LDS.128, one loop over the super rows of a chunk with the shape dispatch inside.
+// in the per-thread shared-memory columns) and ONE static body in which every coefficient of the tape is loaded once and
+// feeds 2|K| DFMAs on |K| independent chains -- image j works on the statically renamed registers x[sigma_j(u)],
+// x[sigma_j(c)], g[...].  Staging as in engines 1 and 3: cp.async double-buffered 16 KB chunks, broadcast LDS.128, one loop over
+// the super rows of a chunk with the shape dispatch inside.  The generated header also carries the row epilogue (inside the
+// shape bodies), the header prefetch macros and the pair-sum variables; this file is the loop around them.
+//
+// The kernel's 420 KB of straight-line bodies pass through the instruction cache once per tile, so HOW the eight warps of the CTA
+// walk the rows matters as much as the instruction count (experiments/README.md section 9): all eight in lock step share every
+// fetched line (hit rate 7/8) but also wait for every miss together; SYM_SPLIT_ORDER 1 (default) lets warps 4..7 walk the rows of
+// each chunk in the cyclic order that starts in the middle, so that the two warps of an SM sub-partition (w and w + 4) miss at
+// different moments: 15.13 -> 14.98 ms.  One start point per warp (8) thrashes the cache: 32.5 ms.
 #pragma once
 #include "mbpol_tape.cuh"
 // acc += a * b with the operand order fixed in PTX (tools/gen_sym.py --asmfma 1)
@@ -21,8 +28,8 @@
 #endif
 #include MBPOL_SYM_HEADER
 
-// own staging buffers: the chunk size of this engine is independent of engines 1 and 3 (smaller chunks leave room for more
-// per-thread columns, i.e. more warps per SM)
+// own staging buffers: the chunk size of this engine is independent of engines 1 and 3 (2048 doubles; 1024 / 1536 / 4096 measured
+// 17.4 / 15.3 / 16.3 ms against 14.8 ms: the chunk also sets how far apart the two halves of the CTA walk)
 extern __constant__ unsigned c_sym_rowvars3b[SYM3B_NROWS * SYM3B_K + SYM_ROWVARS_SPARE];
 extern __constant__ unsigned c_sym_segs3b[SYM3B_NSEGS];
 extern __constant__ int c_sym_chunks3b[SYM3B_NCHUNKS + 1][3];
@@ -78,9 +85,8 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
 #endif
         const unsigned cbase = buf0 + (k & 1) * (SYM_CHUNK_DOUBLES * 8);
         const unsigned row0 = c_sym_chunks3b[k][1], row1 = c_sym_chunks3b[k + 1][1];
-        // The rows of a chunk are independent, so every warp may walk them in its own cyclic order: warps 4..7 start in the middle
-        // of the chunk (SYM_SPLIT_ORDER).  The two warps of an SM sub-partition then run different code most of the time and
-        // miss the instruction cache at different moments -- and each finds the half the other one walked first already fetched.
+        // The rows of a chunk are independent, so a warp may walk them in any cyclic order: warps 4..7 start in the middle of the
+        // chunk (see the head of this file).
         unsigned row = row0;
 #if SYM_SPLIT_ORDER == 1
         if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 2;
@@ -88,8 +94,6 @@ __device__ __forceinline__ void sym_eval3b(const double* __restrict__ tape, doub
         if (threadIdx.x >= TAPE_BS / 2) row += (row1 - row0) / 3;
 #elif SYM_SPLIT_ORDER == 8
         row += ((threadIdx.x >> 5) * (row1 - row0)) / (TAPE_BS / 32);
-#elif SYM_SPLIT_ORDER == 4
-        row += (((threadIdx.x >> 5) & 3) * (row1 - row0)) / 8 + (threadIdx.x >= TAPE_BS / 2 ? (row1 - row0) / 2 : 0);
 #endif
         unsigned row_next = row + 1 == row1 ? row0 : row + 1;
         unsigned cp;
