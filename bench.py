@@ -374,25 +374,30 @@ def main():
     mb.mbpol_compute(h)
     k3 = []
 
-    def step():
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def steps(count):
+        """`count` steps, each bracketed by its own event pair on the library's stream; the L2 flush of the NEXT step is launched
+        right behind a step, so that this rank's bookkeeping (phase times) runs under it and never delays the other ranks at the
+        next collective.  Returns the per-step device times in ms."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
         with torch.cuda.stream(stream):
             flush.zero_()
-            e0.record(stream)
-            mb.mbpol_compute(h)
-            e1.record(stream)
-        e1.synchronize()
-        k3.append(mb.mbpol_phase_times(h))
-        return e0.elapsed_time(e1)
+            for i, (e0, e1) in enumerate(ev):
+                e0.record(stream)
+                mb.mbpol_compute(h)          # (synchronises the stream at its end)
+                e1.record(stream)
+                if i + 1 < count:
+                    flush.zero_()
+                k3.append(mb.mbpol_phase_times(h))
+        torch.cuda.synchronize()
+        return [e0.elapsed_time(e1) for e0, e1 in ev]
 
-    for _ in range(args.warmup):
-        step()
+    steps(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     k3.clear()
-    ms = [step() for _ in range(args.steps)]
+    ms = steps(args.steps)
     barrier()
     counts = mb.mbpol_counts(h)
     t_dev = torch.tensor([sum(ms) / len(ms)], dtype=torch.float64, device="cuda")
