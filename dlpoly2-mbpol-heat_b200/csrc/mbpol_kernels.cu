@@ -580,7 +580,10 @@ struct mbpol_b200_handle {
     struct HostBack { long long counts[4]; double tail[3]; int flag; int pad; } *back = nullptr;     // pinned: read back once per step
     double* host_weight_d = nullptr;           // pinned: per-water load-balancing weights of the previous step (all ranks)
     std::vector<int> host_weight;
-    bool have_weight = false, weights_pending = false, two_streams = false;
+    bool have_weight = false, weights_pending = false, two_streams = false, dbg_times = false;
+    cudaEvent_t dbg_ev = nullptr;
+    double dbg_sum[3] = {0, 0, 0};
+    long long dbg_n = 0, dbg_seen = 0;
     // fused end of mbpol_b200_forces (caller arrays in pinned memory): the caller's current values travel up on vstream while the
     // step runs, the device adds them (k_accumulate) and the sums go straight back into the caller's arrays -- no host "+=" pass
     struct FusedJob { double* dst; size_t off, len; };
@@ -743,6 +746,8 @@ int mbpol_b200_init_batched(int nttm2, int nbeads, int device, int flags, mbpol_
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MBPOL_B200_ECUDA; }
     if (const char* e = std::getenv("MBPOL_B200_TWO_STREAMS")) h->two_streams = std::atoi(e) != 0;
+    if (const char* e = std::getenv("MBPOL_B200_DEBUG_TIMES")) h->dbg_times = std::atoi(e) != 0;
+    if (h->dbg_times) cudaEventCreate(&h->dbg_ev);
     {
         int lo_pri = 0, hi_pri = 0;
         cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
@@ -762,6 +767,10 @@ int mbpol_b200_fini(mbpol_b200_handle* h)
     if (!h) return MBPOL_B200_EINVAL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->dbg_times && h->dbg_n)
+        fprintf(stderr, "mbpol_b200 rank %d: %lld steps, host launch phase %.3f ms, final wait %.3f ms, device time behind the reduction %.3f ms\n",
+                h->rank, h->dbg_n, h->dbg_sum[0] / h->dbg_n, h->dbg_sum[1] / h->dbg_n, h->dbg_sum[2] / h->dbg_n);
+    if (h->dbg_ev) cudaEventDestroy(h->dbg_ev);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -915,6 +924,9 @@ int mbpol_b200_upload(mbpol_b200_handle* h, int imcon, const double* cell, int n
 // from device memory, and an overflow flag (checked after the single synchronisation at the end) triggers a sized retry.
 static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
 {
+    using dclk = std::chrono::steady_clock;
+    const dclk::time_point dbg_t0 = dclk::now();
+    dclk::time_point dbg_t1 = dbg_t0, dbg_t2 = dbg_t0;
     const int nw = h->nw;
     const size_t n = h->mxatms;
     cudaStream_t s = h->stream;
@@ -1108,8 +1120,19 @@ static int compute_once(mbpol_b200_handle* h, bool sized_by_estimate)
         if (!h->host_weight_d) CUDA_TRY(h, cudaMallocHost(&h->host_weight_d, (size_t)(nw + 1) * 8));
         CUDA_TRY(h, cudaMemcpyAsync(h->host_weight_d, h->out.p + h->weight_offset(), (size_t)nw * 8, cudaMemcpyDeviceToHost, s));
     }
+    if (h->dbg_times) CUDA_TRY(h, cudaEventRecord(h->dbg_ev, s));
     CUDA_TRY(h, cudaGetLastError());
+    dbg_t1 = dclk::now();
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    dbg_t2 = dclk::now();
+    if (h->dbg_times && h->fused.empty() && ++h->dbg_seen > 4) {      // MBPOL_B200_DEBUG_TIMES=1 (compute-only steps, after the first four): host wall time of the launch phase and of the final wait, GPU time behind the reduction
+        float tail_ms = 0.f;
+        cudaEventElapsedTime(&tail_ms, h->ev[4], h->dbg_ev);
+        h->dbg_sum[0] += std::chrono::duration<double, std::milli>(dbg_t1 - dbg_t0).count();
+        h->dbg_sum[1] += std::chrono::duration<double, std::milli>(dbg_t2 - dbg_t1).count();
+        h->dbg_sum[2] += tail_ms;
+        ++h->dbg_n;
+    }
     if (h->back->flag == 1) { h->err = "neighbour capacity exceeded (NB2_CAP/NB3_CAP): unphysical density"; return MBPOL_B200_ECAPACITY; }
     if (h->back->tail[2] > 0.0) {      // (all-reduced when a communicator is attached: every rank takes this branch together)
         h->est_nd = h->back->counts[2]; h->est_nt = h->back->counts[3];
