@@ -503,7 +503,10 @@ k_dimers(const long long* __restrict__ pcount, const int2* __restrict__ dim, int
 // (dimer_rows_a) give everything do_dimer accumulates for them (mbpol.f90:519-654, 732-786): force = -row sum, E/6 per atom, W,
 // the (non-symmetric) per-atom stress S_i(a,b) = 1/2 eu sum_j (r_i - r_j)_a FM[i][j]_b, virial / stress / energy scalars.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2)
+#ifndef MBPOL_GATHER2_MINBLOCKS
+#define MBPOL_GATHER2_MINBLOCKS 3      /* 2 / 3 / 4 blocks per SM: 2B phase 3.02 / 2.95 / 3.04 ms */
+#endif
+__global__ void __launch_bounds__(128, MBPOL_GATHER2_MINBLOCKS)
 k_dimers_gather(int nw, const int* __restrict__ inc_off, const unsigned* __restrict__ inc, const int2* __restrict__ dim,
                 const double* __restrict__ rec, const double* __restrict__ mono, const int* __restrict__ list,
                 const double* __restrict__ xr, const double* __restrict__ yr, const double* __restrict__ zr, CellInfo C, OutPtrs O, int flags)
