@@ -103,7 +103,10 @@ int mbpol_b200_host_unregister(void* p);
  *       compute_stress (heatcurrent.f90:703-779) need from the N x N x 3 force_matrix, which is never materialised.
  *   vxx,vyy,vzz (may be NULL) -> jflux[9] is SET to this shard's partial heat-flux contractions:
  *       jflux[0..2] = sum_i e_i v_i, jflux[3..5] = sum_i S_i^{upper-sym} v_i (compute_heat_flux, :464-483),
- *       jflux[6..8] = sum_i W_i v_i (the MB-pol part of jpot in compute_heat_flux2, :703-728). */
+ *       jflux[6..8] = sum_i W_i v_i (the MB-pol part of jpot in compute_heat_flux2, :703-728).
+ * Output arrays in page-locked memory (mbpol_b200_host_register, cudaHostAlloc) take a fused end: their current values are uploaded
+ * while the step runs, added on the device and copied straight back (same "+=" result, no host pass); pageable arrays are staged
+ * and added by host threads.  After a non-zero return the contents of the output arrays are unspecified (the reference aborts). */
 int mbpol_b200_forces(mbpol_b200_handle* handle, int imcon, const double* cell, int nttm2, const int* listttm2,
                       int mxatms, const double* xxx, const double* yyy, const double* zzz,
                       double* fxx, double* fyy, double* fzz,
