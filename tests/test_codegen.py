@@ -244,3 +244,28 @@ def test_generated_sym_header_on_the_host(tmp_path, oracle, env):
             E = lib.sym_host_eval(a.ctypes.data, x.ctypes.data, g.ctypes.data, split)
             assert abs(E - Er) <= 1e-11 * max(abs(Er), np.abs(gr).max())
             assert np.abs(g - gr).max() <= 1e-11 * np.abs(gr).max()
+
+
+def test_default_sym_schedule_is_the_documented_one():
+    """tools/gen_sym.py: the default trie order gives the schedule DESIGN.md / experiments/README.md quote, and the pair-sum merge
+    neither loses nor duplicates a monomial (a merged leaf stands for two monomials of equal coefficient)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_poly
+    import gen_sym
+    mono = np.load(gen_poly.DATA)["mono3b"]
+    order = [int(v) for v in gen_sym.DEFAULT_ORDER.split(",")]
+    rows, shapes, vps = gen_sym.build(mono, "z", True, gen_sym.DEFAULT_REPSEL, order=order)
+    K = len(vps)
+    rows, shapes = gen_sym.merge_pairs(rows)
+    nfp, code, nrows, nshapes = gen_sym.stats(rows, shapes, K)
+    assert (nfp, code, nrows, nshapes) == (71589, 11079, 120, 47)
+    nmono = 0
+    for s, key, children in rows:
+        for us, own, leaves in children:
+            nmono += own[1] if own else 0
+            for cs, k, num in leaves:
+                assert all((c > gen_sym.NV) == (cs[0] > gen_sym.NV) for c in cs)      # an image of a pair sum is a pair sum
+                nmono += num * (2 if cs[0] > gen_sym.NV else 1)
+    assert nmono == len(mono)
+    # every row word field fits its bits (w, v: 6 bits; shape: 7 bits; tape offset / 16: 10 bits)
+    assert nshapes <= 128 and gen_sym.NV + 1 + len(gen_sym.PAIRS) <= 64

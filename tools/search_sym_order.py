@@ -5,7 +5,12 @@ The order decides which variables become the dynamic row pair / the static child
 the number of FP64 instructions per trimer (children and rows cost 4 |K| each) and the size of the generated code (distinct
 row shapes).  Measured on B200 (experiments/README.md section 9): k_trimers time ~ 0.15 ms per 1000 FP64 instructions + 0.043 ms
 per 1000 leaf pairs of code, so the objective is J = instructions + 0.28 * code.  Random-restart hill climbing over swaps and
-moves; prints the best orders found.  usage: search_sym_order.py [seconds] [seed]"""
+moves; prints the best orders found.  usage: search_sym_order.py [seconds] [seed]
+
+The objective only ranks candidates: the instruction cache makes the landscape bumpy (an order with 70.4 k instructions but 15.5 k leaf
+pairs of code runs at 17.6 ms, one with 6.7 k leaf pairs of code and 77.6 k instructions at 32.8 ms with the split row order), so the
+two or three best local optima must be BUILT AND MEASURED (csrc/Makefile: SYMFLAGS="--order ... --repsel ..." OUT=variants/...,
+scripts/ab_phases.py) before one becomes DEFAULT_ORDER in gen_sym.py."""
 import sys
 import time
 
